@@ -1,0 +1,95 @@
+// Shared definitions for the ELG B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/elg_b200.h"
+
+namespace elg {
+
+// Fixed architecture of the released ELG configuration (config.yml model_params).
+constexpr int E = 128;    // embedding_dim
+constexpr int H = 8;      // head_num
+constexpr int D = 16;     // qkv_dim
+constexpr int LE = 32;    // local_att_hidden_dim
+constexpr int LH = 4;     // local_att_head_num
+constexpr int LD = 8;     // local_att_qkv_dim
+constexpr int KT_MAX = 64;  // max local sequence length (local_k + depot)
+
+// ---- derived-table layout (floats), produced by elg_prepare_model --------------------------
+constexpr int DER_WQN = 0;                    // [E][E]  node part of Wq_last
+constexpr int DER_WL = DER_WQN + E * E;       // [E]     load column of Wq_last (cvrp) / zeros
+constexpr int DER_WQF = DER_WL + E;           // [E][E]  Wq_first (tsp) / zeros
+constexpr int DER_WK4 = DER_WQF + E * E;      // [E][E]  Wk / sqrt(D)
+constexpr int DER_WET = DER_WK4 + E * E;      // [E][E]  WET[i][k] = Wo[k][i] / sqrt(E)
+constexpr int DER_BE = DER_WET + E * E;       // [E]     bo / sqrt(E)
+constexpr int DER_LOC = DER_BE + E;           // local-policy tables
+constexpr int LOC_U = 0;                      // [LH][4]      u_h[f]
+constexpr int LOC_T = LOC_U + LH * 4;         // [LH][KT_MAX] t_h[p]
+constexpr int LOC_A = LOC_T + LH * KT_MAX;    // [LE][4]      (Wv We)[c][f]
+constexpr int LOC_CV = LOC_A + LE * 4;        // [LE]         Wv be
+constexpr int LOC_VPE = LOC_CV + LE;          // [KT_MAX][LE] Wv PE(p)
+constexpr int LOC_PE = LOC_VPE + KT_MAX * LE; // [KT_MAX][LE] PE(p)
+constexpr int LOC_WCT = LOC_PE + KT_MAX * LE; // [LE][LE]     WCT[c][c'] = Wo_l[c'][c]
+constexpr int LOC_BC = LOC_WCT + LE * LE;     // [LE]
+constexpr int LOC_WE = LOC_BC + LE;           // [LE][4]      We[c][f]
+constexpr int LOC_BE = LOC_WE + LE * 4;       // [LE]
+constexpr int LOC_TOTAL = LOC_BE + LE;
+constexpr int DER_TOTAL = DER_LOC + LOC_TOTAL;
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_desc(const elg_model_desc* d);
+
+#define ELG_CUDA_OK(call)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (call);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      elg::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                            \
+    }                                                                            \
+  } while (0)
+
+#define ELG_LAUNCH_OK()                                                          \
+  do {                                                                           \
+    elg::count_launch();                                                         \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) {                                                     \
+      elg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                            \
+    }                                                                            \
+  } while (0)
+
+#define ELG_REQUIRE(cond, code, ...)                                             \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      elg::set_error(__VA_ARGS__);                                               \
+      return (code);                                                             \
+    }                                                                            \
+  } while (0)
+
+// ---- device helpers -------------------------------------------------------------------------
+// Euclidean distance exactly as torch's CPU `norm(p=2)` accumulates a 2-vector:
+// acc = dx*dx (rounded); acc = fma(dy, dy, acc); sqrt.  Used everywhere a distance is needed so
+// that neighbour ordering, features and tour lengths all see the same value.
+__device__ __forceinline__ float dist2(float dx, float dy) {
+  return __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// Tour segment length exactly as the reference's reward: ((a-b)**2).sum(-1).sqrt() -- two rounded
+// squares, one rounded add (no fused multiply-add), then sqrt (CVRP/CVRPEnv.py:261, TSP/TSPEnv.py:168).
+__device__ __forceinline__ float seglen(float dx, float dy) {
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+}
+
+// Swizzled column of the score matrix E' (row j): XOR the 16-byte chunk index with (j & 7) so
+// that 8 consecutive rows read by a quarter-warp hit 8 different bank groups.
+__host__ __device__ __forceinline__ int eswz(int j, int c) { return c ^ ((j & 7) << 2); }
+
+// Position of neighbour-list entry e (rank by distance) inside a node's ELG_NBR_STRIDE-byte row:
+// 8-way interleaved so lane s of an octet reads its entries e = s, s+8, ... with one 16-byte load.
+__host__ __device__ __forceinline__ int nbr_pos(int e) { return (e & 7) * 16 + (e >> 3); }
+
+}  // namespace elg

@@ -1,0 +1,331 @@
+// Encoder (model.pre_forward) and the decoder-side tables derived from the encoded nodes.
+//
+// reference: CVRP_Encoder / EncoderLayer / AddAndInstanceNormalization / FeedForward
+//            (CVRP/models.py:199-269,506-562), TSP twins (TSP/models.py:134-194,387-423),
+//            decoder.set_kv (CVRP/models.py:300-308, TSP/models.py:227-235).
+//
+// All encoder linears are batched over the B*N1 node rows of the whole batch so the 0.8 M
+// weights are read once per batch (weight-stationary tiles), fp32 FMA accumulation (TF32/BF16
+// inputs would break the 1e-4 logit tolerance).  Per layer:
+//   qkv  = x [Wq;Wk;Wv]^T                     sgemm, N = 384
+//   att  = softmax(q k^T / 4) v               per (aug-instance, head), K/V staged in smem
+//   t    = att Wo^T + bo + x                  sgemm + bias + residual epilogue
+//   x1   = instance_norm(t) * w + b           per aug-instance, stats over nodes
+//   hid  = relu(x1 W1^T + b1)                 sgemm + bias + relu epilogue
+//   t    = hid W2^T + b2 + x1                 sgemm + bias + residual epilogue
+//   x    = instance_norm(t) * w + b
+#include "common.cuh"
+
+namespace elg {
+
+int launch_neighbours(int problem, const float* xy, int B, int N1, uint8_t* nbr, cudaStream_t stream);
+
+// ---- embedding --------------------------------------------------------------------------------
+__global__ void embed_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand,
+                             const float* __restrict__ w, elg_weight_layout_t L, long long rows, int N1,
+                             float* __restrict__ x) {
+  const long long total = rows * E;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(idx % E);
+    long long r = idx / E;
+    int j = (int)(r % N1);
+    float px = xy[2 * r], py = xy[2 * r + 1];
+    float v;
+    if (problem == ELG_CVRP) {
+      if (j == 0) {
+        // F.linear: x0*w0 + x1*w1 then + bias
+        v = fmaf(py, w[L.emb_depot_w + c * 2 + 1], px * w[L.emb_depot_w + c * 2]) + w[L.emb_depot_b + c];
+      } else {
+        v = fmaf(demand[r], w[L.emb_node_w + c * 3 + 2],
+                 fmaf(py, w[L.emb_node_w + c * 3 + 1], px * w[L.emb_node_w + c * 3])) + w[L.emb_node_b + c];
+      }
+    } else {
+      v = fmaf(py, w[L.emb_node_w + c * 2 + 1], px * w[L.emb_node_w + c * 2]) + w[L.emb_node_b + c];
+    }
+    x[idx] = v;
+  }
+}
+
+// ---- SGEMM  C[M][N] = A[M][K] * B[N][K]^T (+ epilogue) ----------------------------------------
+// 128x128x8 tiles, 256 threads, 8x8 register tile per thread, register-prefetched double buffer.
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RES = 3, EPI_SWIZZLE = 4 };
+
+template <int EPI>
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                       float* __restrict__ C, const float* __restrict__ bias,
+                                                       const float* __restrict__ res, long long M, int N, int K,
+                                                       int ldc, int N1) {
+  constexpr int BM = 128, BN = 128, BK = 8;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int lrow = tid >> 1, lk = (tid & 1) * 4;      // each thread loads one float4 of A and of B per k-tile
+  const int ty = tid >> 4, tx = tid & 15;             // 16 x 16 threads, 8 x 8 outputs each
+  const long long arow = m0 + lrow;
+  const bool a_ok = arow < M;
+  const float* ap = A + (a_ok ? arow : 0) * (long long)K + lk;
+  const float* bp = Bm + (long long)(n0 + lrow) * K + lk;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra = a_ok ? *reinterpret_cast<const float4*>(ap) : make_float4(0, 0, 0, 0);
+  float4 rb = *reinterpret_cast<const float4*>(bp);
+  As[0][lk + 0][lrow] = ra.x; As[0][lk + 1][lrow] = ra.y; As[0][lk + 2][lrow] = ra.z; As[0][lk + 3][lrow] = ra.w;
+  Bs[0][lk + 0][lrow] = rb.x; Bs[0][lk + 1][lrow] = rb.y; Bs[0][lk + 2][lrow] = rb.z; Bs[0][lk + 3][lrow] = rb.w;
+  __syncthreads();
+  const int nk = K / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      ra = a_ok ? *reinterpret_cast<const float4*>(ap + (kt + 1) * BK) : make_float4(0, 0, 0, 0);
+      rb = *reinterpret_cast<const float4*>(bp + (kt + 1) * BK);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      const int nx = cur ^ 1;
+      As[nx][lk + 0][lrow] = ra.x; As[nx][lk + 1][lrow] = ra.y; As[nx][lk + 2][lrow] = ra.z; As[nx][lk + 3][lrow] = ra.w;
+      Bs[nx][lk + 0][lrow] = rb.x; Bs[nx][lk + 1][lrow] = rb.y; Bs[nx][lk + 2][lrow] = rb.z; Bs[nx][lk + 3][lrow] = rb.w;
+    }
+    __syncthreads();
+  }
+  // epilogue: rows m0 + {ty*4+i, 64+ty*4+i}, cols n0 + {tx*4+j, 64+tx*4+j}
+#pragma unroll
+  for (int ih = 0; ih < 2; ++ih)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = m0 + ih * 64 + ty * 4 + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        const int n = n0 + jh * 64 + tx * 4;
+        float4 v = make_float4(acc[ih * 4 + i][jh * 4 + 0], acc[ih * 4 + i][jh * 4 + 1], acc[ih * 4 + i][jh * 4 + 2],
+                               acc[ih * 4 + i][jh * 4 + 3]);
+        if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES) {
+          float4 bb = *reinterpret_cast<const float4*>(bias + n);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        if (EPI == EPI_BIAS_RELU) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        if (EPI == EPI_BIAS_RES) {
+          float4 rr = *reinterpret_cast<const float4*>(res + m * ldc + n);
+          v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+        }
+        int nn = n;
+        if (EPI == EPI_SWIZZLE) nn = eswz((int)(m % N1), n);
+        *reinterpret_cast<float4*>(C + m * ldc + nn) = v;
+      }
+    }
+}
+
+// ---- encoder self-attention: one CTA per (aug-instance, head) --------------------------------------
+// qkv rows are [q(128) | k(128) | v(128)]; scores q.k/4, softmax over keys, weighted values.
+constexpr int ATT_TK = 512;     // keys staged per tile (64 KB of K+V)
+__global__ void __launch_bounds__(128) enc_attention_kernel(const float* __restrict__ qkv, int N1,
+                                                            float* __restrict__ att) {
+  extern __shared__ __align__(16) float sm[];
+  float* sk = sm;                      // [ATT_TK][16]
+  float* sv = sm + ATT_TK * D;         // [ATT_TK][16]
+  const int h = blockIdx.x % H;
+  const long long b = blockIdx.x / H;
+  const float* base = qkv + b * N1 * (3LL * E);
+  for (int i0 = 0; i0 < N1; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool ok = i < N1;
+    float q[D], o[D];
+    float m = -INFINITY, l = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      float4 t = ok ? *reinterpret_cast<const float4*>(base + (long long)i * 3 * E + h * D + d4 * 4) : make_float4(0, 0, 0, 0);
+      q[d4 * 4] = t.x * 0.25f; q[d4 * 4 + 1] = t.y * 0.25f; q[d4 * 4 + 2] = t.z * 0.25f; q[d4 * 4 + 3] = t.w * 0.25f;
+      o[d4 * 4] = o[d4 * 4 + 1] = o[d4 * 4 + 2] = o[d4 * 4 + 3] = 0.f;
+    }
+    for (int j0 = 0; j0 < N1; j0 += ATT_TK) {
+      const int nj = min(ATT_TK, N1 - j0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < nj * (D / 4); t += blockDim.x) {
+        int j = t / (D / 4), d4 = t % (D / 4);
+        const float* rowp = base + (long long)(j0 + j) * 3 * E + h * D + d4 * 4;
+        *reinterpret_cast<float4*>(sk + j * D + d4 * 4) = *reinterpret_cast<const float4*>(rowp + E);
+        *reinterpret_cast<float4*>(sv + j * D + d4 * 4) = *reinterpret_cast<const float4*>(rowp + 2 * E);
+      }
+      __syncthreads();
+      for (int j = 0; j < nj; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+          float4 kk = *reinterpret_cast<const float4*>(sk + j * D + d4 * 4);
+          s = fmaf(q[d4 * 4], kk.x, s); s = fmaf(q[d4 * 4 + 1], kk.y, s);
+          s = fmaf(q[d4 * 4 + 2], kk.z, s); s = fmaf(q[d4 * 4 + 3], kk.w, s);
+        }
+        if (s > m + 8.f) {           // lazy rescale: only when the running reference falls far behind
+          float c = expf(m - s);
+          l *= c;
+#pragma unroll
+          for (int d = 0; d < D; ++d) o[d] *= c;
+          m = s;
+        }
+        float p = expf(s - m);
+        l += p;
+#pragma unroll
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+          float4 vv = *reinterpret_cast<const float4*>(sv + j * D + d4 * 4);
+          o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
+          o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
+        }
+      }
+    }
+    if (ok) {
+      const float inv = 1.f / l;
+      float* op = att + (b * N1 + i) * E + h * D;
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4)
+        *reinterpret_cast<float4*>(op + d4 * 4) =
+            make_float4(o[d4 * 4] * inv, o[d4 * 4 + 1] * inv, o[d4 * 4 + 2] * inv, o[d4 * 4 + 3] * inv);
+    }
+  }
+}
+
+// ---- instance norm over the nodes of one aug-instance (input already holds x + sublayer(x)) -------
+// nn.InstanceNorm1d(E, affine=True, track_running_stats=False): biased variance, eps 1e-5.
+__global__ void __launch_bounds__(E) instance_norm_kernel(const float* __restrict__ t, const float* __restrict__ w,
+                                                          const float* __restrict__ bsh, int N1,
+                                                          float* __restrict__ out) {
+  const long long b = blockIdx.x;
+  const int c = threadIdx.x;
+  const float* p = t + b * N1 * E + c;
+  float s = 0.f;
+  for (int n = 0; n < N1; ++n) s += p[(long long)n * E];
+  const float mean = s / (float)N1;
+  float v = 0.f;
+  for (int n = 0; n < N1; ++n) {
+    float d = p[(long long)n * E] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = 1.f / sqrtf(v / (float)N1 + 1e-5f);
+  const float g = w[c], be = bsh[c];
+  float* q = out + b * N1 * E + c;
+  for (int n = 0; n < N1; ++n) q[(long long)n * E] = (p[(long long)n * E] - mean) * rstd * g + be;
+}
+
+// ---- score bias eb[r] = enc[r] . (bo / sqrt(E)) : one warp per node row -----------------------------
+__global__ void row_dot_kernel(const float* __restrict__ x, const float* __restrict__ v, long long rows,
+                               float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  float4 a = *reinterpret_cast<const float4*>(x + r * E + lane * 4);
+  float4 bq = *reinterpret_cast<const float4*>(v + lane * 4);
+  float s = a.x * bq.x;
+  s = fmaf(a.y, bq.y, s); s = fmaf(a.z, bq.z, s); s = fmaf(a.w, bq.w, s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = s;
+}
+
+template <int EPI>
+static int gemm(const float* A, const float* Bm, float* C, const float* bias, const float* res, long long M, int N,
+                int K, int ldc, int N1, cudaStream_t st) {
+  ELG_REQUIRE(N % 128 == 0 && K % 8 == 0, ELG_EUNSUPPORTED, "sgemm needs N%%128==0 and K%%8==0 (N=%d K=%d)", N, K);
+  dim3 grid((unsigned)((M + 127) / 128), N / 128);
+  sgemm_tn_kernel<EPI><<<grid, 256, 0, st>>>(A, Bm, C, bias, res, M, N, K, ldc, N1);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace elg
+
+using namespace elg;
+
+extern "C" {
+
+size_t elg_encode_workspace_bytes(const elg_model_desc* d, int B, int N1) {
+  if (check_desc(d) || B <= 0 || N1 <= 0) return 0;
+  size_t rows = (size_t)B * N1;
+  // x, x1, t (E each), att (E), qkv (3E), hid (ff)
+  return align_up(rows * (size_t)(E * 4 + 3 * E + d->ff) * sizeof(float), 256) + 256;
+}
+
+#define ELG_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+int elg_encode(const elg_model_desc* d, const float* weights, const float* derived, const elg_tables* t, int B,
+               int N1, void* workspace, size_t workspace_bytes, void* stream) {
+  elg_weight_layout_t L;
+  ELG_TRY(elg_weight_layout(d, &L));
+  ELG_REQUIRE(weights && derived && t && workspace, ELG_EINVAL, "NULL pointer");
+  ELG_REQUIRE(B > 0 && N1 > 1, ELG_EINVAL, "bad batch/node count");
+  ELG_REQUIRE(t->xy && t->enc && t->k && t->v && t->e && t->eb && t->qtab, ELG_EINVAL, "elg_tables has NULL members");
+  ELG_REQUIRE(d->problem == ELG_TSP ? t->qfirst != nullptr : t->demand != nullptr, ELG_EINVAL,
+              "tsp needs qfirst, cvrp needs demand");
+  ELG_REQUIRE(workspace_bytes >= elg_encode_workspace_bytes(d, B, N1), ELG_ENOMEM, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)B * N1;
+  float* x = reinterpret_cast<float*>(align_up((size_t)workspace, 256));
+  float* x1 = x + rows * E;
+  float* tt = x1 + rows * E;
+  float* att = tt + rows * E;
+  float* qkv = att + rows * E;
+  float* hid = qkv + rows * 3 * E;
+  const float* w = weights;
+
+  {
+    long long total = rows * E;
+    int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    embed_kernel<<<grid, 256, 0, st>>>(d->problem, t->xy, t->demand, w, L, rows, N1, x);
+    ELG_LAUNCH_OK();
+  }
+  static bool attr_set = false;
+  const int att_smem = 2 * ATT_TK * D * (int)sizeof(float);
+  if (!attr_set) {
+    ELG_CUDA_OK(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem));
+    attr_set = true;
+  }
+  for (int l = 0; l < d->layers; ++l) {
+    const auto& y = L.layer[l];
+    float* xout = (l == d->layers - 1) ? t->enc : x;
+    ELG_TRY(gemm<EPI_NONE>(x, w + y.wq, qkv, nullptr, nullptr, rows, 3 * E, E, 3 * E, N1, st));
+    enc_attention_kernel<<<(unsigned)(B * H), 128, att_smem, st>>>(qkv, N1, att);
+    ELG_LAUNCH_OK();
+    ELG_TRY(gemm<EPI_BIAS_RES>(att, w + y.wo, tt, w + y.bo, x, rows, E, E, E, N1, st));
+    instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n1w, w + y.n1b, N1, x1);
+    ELG_LAUNCH_OK();
+    ELG_TRY(gemm<EPI_BIAS_RELU>(x1, w + y.w1, hid, w + y.b1, nullptr, rows, d->ff, E, d->ff, N1, st));
+    ELG_TRY(gemm<EPI_BIAS_RES>(hid, w + y.w2, tt, w + y.b2, x1, rows, E, d->ff, E, N1, st));
+    instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n2w, w + y.n2b, N1, xout);
+    ELG_LAUNCH_OK();
+  }
+  // decoder-side tables from the encoded nodes
+  const float* enc = t->enc;
+  ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WK4, t->k, nullptr, nullptr, rows, E, E, E, N1, st));
+  ELG_TRY(gemm<EPI_NONE>(enc, w + L.dec_wv, t->v, nullptr, nullptr, rows, E, E, E, N1, st));
+  ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, t->e, nullptr, nullptr, rows, E, E, E, N1, st));
+  ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQN, t->qtab, nullptr, nullptr, rows, E, E, E, N1, st));
+  if (d->problem == ELG_TSP)
+    ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQF, t->qfirst, nullptr, nullptr, rows, E, E, E, N1, st));
+  row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
+  ELG_LAUNCH_OK();
+  if (t->nbr && N1 <= ELG_MAX_NODES_RESIDENT) ELG_TRY(launch_neighbours(d->problem, t->xy, B, N1, t->nbr, st));
+  return ELG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// Problem loading (x8 augmentation), neighbour lists, environment step on bit masks,
+// per-step features (API compatibility) and tour length.
+#include "common.cuh"
+
+namespace elg {
+
+// ---- x8 augmentation + depot/node concatenation ---------------------------------------------
+// reference: augment_xy_data_by_8_fold (CVRP/utils.py:69-87), load_random_problems (CVRP/CVRPEnv.py:125-150)
+__global__ void load_problems_kernel(int problem, const float* __restrict__ depot, const float* __restrict__ nodes,
+                                     const float* __restrict__ demand, int n, int n_nodes, int aug,
+                                     float* __restrict__ xy_out, float* __restrict__ dem_out) {
+  const int N1 = n_nodes + (problem == ELG_CVRP ? 1 : 0);
+  const long long total = (long long)aug * n * N1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(idx % N1);
+    long long bi = idx / N1;
+    int i = (int)(bi % n), a = (int)(bi / n);
+    float x, y, dm = 0.f;
+    if (problem == ELG_CVRP && j == 0) {
+      x = depot[2 * i]; y = depot[2 * i + 1];
+    } else {
+      int jj = j - (problem == ELG_CVRP ? 1 : 0);
+      x = nodes[((long long)i * n_nodes + jj) * 2];
+      y = nodes[((long long)i * n_nodes + jj) * 2 + 1];
+      if (demand) dm = demand[(long long)i * n_nodes + jj];
+    }
+    float ox, oy;
+    switch (a) {
+      case 0: ox = x; oy = y; break;
+      case 1: ox = 1.f - x; oy = y; break;
+      case 2: ox = x; oy = 1.f - y; break;
+      case 3: ox = 1.f - x; oy = 1.f - y; break;
+      case 4: ox = y; oy = x; break;
+      case 5: ox = 1.f - y; oy = x; break;
+      case 6: ox = y; oy = 1.f - x; break;
+      default: ox = 1.f - y; oy = 1.f - x; break;
+    }
+    xy_out[idx * 2] = ox;
+    xy_out[idx * 2 + 1] = oy;
+    if (dem_out) dem_out[idx] = dm;
+  }
+}
+
+__global__ void pairwise_dist_kernel(const float* __restrict__ xy, int B, int N1, float* __restrict__ out) {
+  const long long total = (long long)B * N1 * N1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(idx % N1);
+    long long bi = idx / N1;
+    int i = (int)(bi % N1);
+    long long b = bi / N1;
+    const float* p = xy + b * N1 * 2;
+    out[idx] = dist2(p[2 * i] - p[2 * j], p[2 * i + 1] - p[2 * j + 1]);
+  }
+}
+
+// ---- neighbour lists ------------------------------------------------------------------------
+// For every node i of every aug-instance: all candidate nodes (customers 1..N for cvrp, every node
+// for tsp) ordered by (distance from i, index).  The decode step takes the first k *valid* entries,
+// which is what torch.topk(k, largest=False) over the masked distance row yields in the reference
+// (CVRP/models.py:74,375; TSP/models.py:62,286) -- computed once instead of twice per step.
+__global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int N1, uint8_t* __restrict__ nbr) {
+  __shared__ float sd[ELG_MAX_NODES_RESIDENT];
+  const int i = blockIdx.x % N1, b = blockIdx.x / N1;
+  const float* p = xy + (size_t)b * N1 * 2;
+  const int j0 = problem == ELG_CVRP ? 1 : 0;
+  const float xi = p[2 * i], yi = p[2 * i + 1];
+  for (int j = threadIdx.x; j < N1; j += blockDim.x) sd[j] = dist2(xi - p[2 * j], yi - p[2 * j + 1]);
+  uint8_t* row = nbr + ((size_t)b * N1 + i) * ELG_NBR_STRIDE;
+  for (int e = threadIdx.x; e < ELG_NBR_STRIDE; e += blockDim.x) row[e] = 0;
+  __syncthreads();
+  for (int j = j0 + threadIdx.x; j < N1; j += blockDim.x) {
+    float dj = sd[j];
+    int rank = 0;
+    for (int k = j0; k < N1; ++k) {
+      float dk = sd[k];
+      rank += (dk < dj) || (dk == dj && k < j);
+    }
+    row[nbr_pos(rank)] = (uint8_t)j;
+  }
+}
+
+// ---- environment step on bit masks (one warp per row) -----------------------------------------
+// reference: CVRPEnv.step (CVRP/CVRPEnv.py:190-249), TSPEnv.step (TSP/TSPEnv.py:108-133)
+__global__ void env_step_kernel(int problem, const float* __restrict__ demand, int B, int M, int N1,
+                                const int32_t* __restrict__ selected, float* __restrict__ load,
+                                uint32_t* __restrict__ visited, uint32_t* __restrict__ mask,
+                                uint8_t* __restrict__ finished, float* __restrict__ ninf_mask,
+                                int32_t* __restrict__ n_unfinished) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * M) return;
+  const int b = (int)(row / M);
+  const int sel = selected[row];
+  uint32_t vis[4], msk[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) vis[w] = visited[row * 4 + w];
+  vis[sel >> 5] |= 1u << (sel & 31);
+  bool fin = false;
+  if (problem == ELG_CVRP) {
+    const float* dem = demand + (size_t)b * N1;
+    const bool at_depot = sel == 0;
+    float ld = load[row];
+    ld = at_depot ? 1.f : ld - dem[sel];
+    if (at_depot) vis[0] |= 1u; else vis[0] &= ~1u;
+    bool all_vis = true;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      int j = w * 32 + lane;
+      bool big = j < N1 && (__fadd_rn(ld, 1e-6f) < dem[j]);
+      uint32_t bw = __ballot_sync(0xffffffffu, big);
+      msk[w] = vis[w] | bw;
+      int nb = N1 - w * 32;
+      uint32_t full = nb >= 32 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+      all_vis = all_vis && ((vis[w] & full) == full);
+    }
+    fin = finished[row] || all_vis;
+    if (fin) msk[0] &= ~1u;
+    if (lane == 0) { load[row] = ld; finished[row] = fin ? 1 : 0; }
+  } else {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) msk[w] = vis[w];
+  }
+  if (lane < 4) {
+    visited[row * 4 + lane] = vis[lane];
+    mask[row * 4 + lane] = msk[lane];
+  }
+  if (ninf_mask) {
+    for (int j = lane; j < N1; j += 32)
+      ninf_mask[row * N1 + j] = ((msk[j >> 5] >> (j & 31)) & 1u) ? -INFINITY : 0.f;
+  }
+  if (n_unfinished && lane == 0 && problem == ELG_CVRP && !fin) atomicAdd(n_unfinished, 1);
+}
+
+// ---- per-step features (API compatibility only; the decode kernel recomputes what it needs) ----
+// reference: CVRPEnv.get_cur_feature (CVRP/CVRPEnv.py:291-318), TSPEnv.get_local_feature (TSP/TSPEnv.py:135-156)
+__global__ void cur_feature_kernel(const float* __restrict__ xy, const float* __restrict__ demand,
+                                   const float* __restrict__ load, const int32_t* __restrict__ cur, int B, int M,
+                                   int N1, float* __restrict__ cur_dist, float* __restrict__ cur_theta,
+                                   float* __restrict__ rel_xy, float* __restrict__ norm_demand) {
+  const long long total = (long long)B * M * N1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(idx % N1);
+    long long row = idx / N1;
+    long long b = row / M;
+    const float* p = xy + b * N1 * 2;
+    int c = cur[row];
+    float rx = p[2 * j] - p[2 * c], ry = p[2 * j + 1] - p[2 * c + 1];
+    cur_dist[idx] = dist2(p[2 * c] - p[2 * j], p[2 * c + 1] - p[2 * j + 1]);
+    cur_theta[idx] = atan2f(ry, rx);
+    rel_xy[idx * 2] = rx;
+    rel_xy[idx * 2 + 1] = ry;
+    if (norm_demand) norm_demand[idx] = demand[b * N1 + j] / load[row];
+  }
+}
+
+// ---- closed-tour length -----------------------------------------------------------------------
+// reference: _get_reward / compute_unscaled_reward (CVRP/CVRPEnv.py:251-288),
+//            _get_travel_distance / compute_unscaled_distance (TSP/TSPEnv.py:158-184)
+__global__ void tour_length_kernel(const float* __restrict__ xy, int Bxy, const int64_t* __restrict__ tours, int B,
+                                   int M, int T, int N1, int round_edges, float* __restrict__ out) {
+  const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (row >= (long long)B * M) return;
+  const long long b = row / M;
+  const float* p = xy + (Bxy == 1 ? 0 : b) * (long long)N1 * 2;
+  const int64_t* t = tours + row * T;
+  int first = (int)t[0], prev = first;
+  float sum = 0.f;
+  for (int s = 1; s <= T; ++s) {
+    int nxt = s < T ? (int)t[s] : first;
+    float d = seglen(p[2 * prev] - p[2 * nxt], p[2 * prev + 1] - p[2 * nxt + 1]);
+    if (round_edges) d = rintf(d);
+    sum += d;
+    prev = nxt;
+  }
+  out[row] = sum;
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  return (int)(g > 148LL * 32 ? 148 * 32 : (g < 1 ? 1 : g));
+}
+
+}  // namespace elg
+
+using namespace elg;
+
+extern "C" {
+
+int elg_load_problems(int problem, const float* depot_xy, const float* node_xy, const float* node_demand, int n,
+                      int n_nodes, int aug, float* xy_out, float* demand_out, void* stream) {
+  ELG_REQUIRE(problem == ELG_TSP || problem == ELG_CVRP, ELG_EINVAL, "unknown problem %d", problem);
+  ELG_REQUIRE(aug == 1 || aug == 8, ELG_EUNSUPPORTED, "aug_factor must be 1 or 8 (got %d)", aug);
+  ELG_REQUIRE(n > 0 && n_nodes > 0 && node_xy && xy_out, ELG_EINVAL, "bad sizes/pointers");
+  ELG_REQUIRE(problem == ELG_TSP || (depot_xy && node_demand && demand_out), ELG_EINVAL, "cvrp needs depot/demand");
+  const int N1 = n_nodes + (problem == ELG_CVRP ? 1 : 0);
+  long long total = (long long)aug * n * N1;
+  load_problems_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      problem, depot_xy, node_xy, problem == ELG_CVRP ? node_demand : nullptr, n, n_nodes, aug, xy_out,
+      problem == ELG_CVRP ? demand_out : nullptr);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+int elg_pairwise_dist(const float* xy, int B, int N1, float* dist_out, void* stream) {
+  ELG_REQUIRE(xy && dist_out && B > 0 && N1 > 0, ELG_EINVAL, "bad sizes/pointers");
+  pairwise_dist_kernel<<<grid_for((long long)B * N1 * N1, 256), 256, 0, (cudaStream_t)stream>>>(xy, B, N1, dist_out);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+int elg_env_step(int problem, const float* demand, int B, int M, int N1, const int32_t* selected, float* load,
+                 uint32_t* visited_bits, uint32_t* mask_bits, uint8_t* finished, float* ninf_mask,
+                 int32_t* n_unfinished, void* stream) {
+  ELG_REQUIRE(problem == ELG_TSP || problem == ELG_CVRP, ELG_EINVAL, "unknown problem %d", problem);
+  ELG_REQUIRE(N1 > 0 && N1 <= 128, ELG_EUNSUPPORTED, "bit-mask env supports up to 128 nodes (got %d)", N1);
+  ELG_REQUIRE(selected && visited_bits && mask_bits, ELG_EINVAL, "NULL state pointer");
+  ELG_REQUIRE(problem == ELG_TSP || (demand && load && finished), ELG_EINVAL, "cvrp needs demand/load/finished");
+  long long threads = (long long)B * M * 32;
+  env_step_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      problem, demand, B, M, N1, selected, load, visited_bits, mask_bits, finished, ninf_mask, n_unfinished);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+int elg_cur_feature(const float* xy, const float* demand, const float* load, const int32_t* cur, int B, int M,
+                    int N1, float* cur_dist, float* cur_theta, float* rel_xy, float* norm_demand, void* stream) {
+  ELG_REQUIRE(xy && cur && cur_dist && cur_theta && rel_xy, ELG_EINVAL, "NULL pointer");
+  ELG_REQUIRE(!norm_demand || (demand && load), ELG_EINVAL, "norm_demand needs demand and load");
+  cur_feature_kernel<<<grid_for((long long)B * M * N1, 256), 256, 0, (cudaStream_t)stream>>>(
+      xy, demand, load, cur, B, M, N1, cur_dist, cur_theta, rel_xy, norm_demand);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M, int T, int N1, int round_edges,
+                    float* out, void* stream) {
+  ELG_REQUIRE(xy && tours && out && T > 0, ELG_EINVAL, "bad sizes/pointers");
+  ELG_REQUIRE(Bxy == 1 || Bxy == B, ELG_EINVAL, "xy batch must be 1 or B");
+  long long rows = (long long)B * M;
+  tour_length_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(xy, Bxy, tours, B, M, T, N1,
+                                                                                        round_edges, out);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+}  // extern "C"
+
+// neighbour lists are built by elg_encode (encoder.cu) through this launcher
+namespace elg {
+int launch_neighbours(int problem, const float* xy, int B, int N1, uint8_t* nbr, cudaStream_t stream) {
+  ELG_REQUIRE(N1 <= ELG_MAX_NODES_RESIDENT, ELG_EUNSUPPORTED, "neighbour lists support up to %d nodes", ELG_MAX_NODES_RESIDENT);
+  neighbour_kernel<<<(unsigned)B * N1, 128, 0, stream>>>(problem, xy, N1, nbr);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+}  // namespace elg

@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libelg_b200.so), against
+  * the golden vectors recorded from the unmodified reference (tests/golden), and
+  * the CPU oracle (fp32 restatement, and its fp64 evaluation as "truth") on fresh seeded inputs.
+
+Bars: bit-exact for integer/byte state (masks, visited, finished, loads under teacher forcing,
+tours where the reference's own top-2 logit margin exceeds the fp32 noise floor); logits within
+2e-3 absolute on the [-50, 50] clipping range (north_star: 1e-4 relative = 5e-3) and no worse
+against fp64 truth than the reference itself; tour lengths within 1e-4 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_CASES, CVRP_CASES, TSP_CASES, Golden, compare_tours, sub_problem, top2_margin
+from oracle import elg_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+LOGIT_MAX_ATOL = 2e-3
+LOGIT_MEAN_ATOL = 3e-5
+
+
+def _setup(g):
+    from elg_b200 import engine
+    handle = engine.ModelHandle(g.kind, g.model_params(), g.state_dict(), DEV)
+    prob = g.oracle_problem()
+    xy = prob.xy.to(DEV)
+    dem = None if prob.demand is None else prob.demand.to(DEV)
+    batch = engine.encode(handle, xy, dem)
+    return engine, handle, prob, batch
+
+
+@pytest.fixture(scope="module", params=ALL_CASES)
+def case(request):
+    g = Golden(request.param)
+    return (g,) + _setup(g)
+
+
+def test_encoder_matches_reference(case):
+    g, engine, handle, prob, batch = case
+    ref = torch.tensor(g.z["enc"])
+    got = batch.enc[g.rows_b].cpu()
+    assert (got - ref).abs().max() < 5e-5
+
+
+def test_teacher_forced_logits_and_choices(case):
+    g, engine, handle, prob, batch = case
+    rows = g.rows_b
+    sub = engine.encode(handle, batch.xy[rows], None if batch.demand is None else batch.demand[rows])
+    first = g.tours()[rows][:, :, 0].to(DEV) if g.kind == "tsp" else None
+    worst, total, count, flips, decisions = 0.0, 0.0, 0, 0, 0
+    for t in g.steps:
+        s = g.step(t)
+        bits = engine.pack_mask_bits(s["masked"].to(DEV))
+        sel, _, logits = engine.decode_step(sub, g.M, s["cur"].to(DEV), bits,
+                                            load=None if g.kind == "tsp" else s["load"].to(DEV), first=first,
+                                            want_logits=True)
+        logits, sel = logits.cpu(), sel.cpu()
+        ref = s["logits"]
+        live = torch.ones(ref.shape[:2], dtype=torch.bool) if g.kind == "tsp" else ~s["finished"]
+        assert torch.equal(torch.isinf(logits)[live], torch.isinf(ref)[live])
+        fin = ~torch.isinf(ref) & live[:, :, None]
+        err = (logits[fin] - ref[fin]).abs()
+        worst, total, count = max(worst, float(err.max())), total + float(err.sum()), count + err.numel()
+        clear = (top2_margin(ref) > 2 * LOGIT_MAX_ATOL) & live
+        assert torch.equal(sel[clear], s["selected"][clear])
+        flips += int((sel[live] != s["selected"][live]).sum())
+        decisions += int(live.sum())
+    assert worst < LOGIT_MAX_ATOL, worst
+    assert total / count < LOGIT_MEAN_ATOL, total / count
+    assert flips <= max(1, decisions // 2000), (flips, decisions)
+
+
+def test_fused_rollout_matches_reference_tours(case):
+    g, engine, handle, prob, batch = case
+    unscaled = None
+    if g.meta.get("lib"):
+        unscaled = prob.unscaled_xy.expand(batch.B, -1, -1).contiguous().to(DEV)
+        batch.tables.unscaled = unscaled.data_ptr()
+    tours16, reward, _, n_steps = engine.rollout(batch, g.M, g.perm().tolist())
+    T = int(n_steps.max())
+    tours = tours16[:, :, :T].long().cpu()
+    ref_t, ref_r = g.tours(), g.reward()
+    frac, same = compare_tours(tours, ref_t)
+    assert frac >= 0.97, frac
+    rel = ((reward.cpu() - ref_r).abs() / ref_r.abs())[same]
+    assert rel.max() < 1e-4
+    if g.meta.get("lib"):
+        assert torch.equal(reward.cpu()[same], ref_r[same])            # rounded integer costs: exact
+    if same.all():
+        assert T == g.T
+    # every tour, matching or not, must be feasible and its reward must be its own length
+    if g.kind == "cvrp":
+        O.check_feasible_cvrp(tours, prob.demand)
+    else:
+        assert torch.equal(tours.sort(dim=2)[0], torch.arange(prob.xy.shape[1]).expand_as(tours))
+    if g.meta.get("lib"):
+        xy = prob.unscaled_xy.expand(batch.B, -1, -1) if g.kind == "tsp" else prob.unscaled_xy
+        assert torch.equal(-O.tour_length(xy, tours, rounding=True), reward.cpu())
+    else:
+        assert (O.tour_length(prob.xy, tours) + reward.cpu()).abs().max() < 2e-5
+    # best-of-POMO / best-of-aug cost agrees with the reference's
+    if g.aug == 8:
+        n = batch.B // 8
+        _, got_aug = O.best_of(reward.cpu(), 8, n)
+        _, ref_aug = O.best_of(ref_r, 8, n)
+        assert ((got_aug - ref_aug).abs() / ref_aug.abs()).max() < 2e-3
+
+
+def test_env_step_bit_exact(case):
+    """Replay the reference's tours through elg_env_step: loads, masks and finished flags bit-exact."""
+    g, engine, handle, prob, batch = case
+    tours = g.tours().to(DEV)
+    B, M, T = tours.shape
+    N1 = prob.xy.shape[1]
+    load = torch.ones((B, M), device=DEV)
+    vis = torch.zeros((B, M, 4), dtype=torch.int32, device=DEV)
+    msk = torch.zeros((B, M, 4), dtype=torch.int32, device=DEV)
+    fin = torch.zeros((B, M), dtype=torch.uint8, device=DEV)
+    ninf = torch.zeros((B, M, N1), device=DEV)
+    cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for t in range(T):
+        if t in g.steps:
+            s = g.step(t)
+            assert torch.equal(torch.isinf(ninf[g.rows_b]).cpu(), s["masked"])
+            assert torch.equal(engine.pack_mask_bits(s["masked"].to(DEV)), msk[g.rows_b])
+            if g.kind == "cvrp":
+                assert torch.equal(load[g.rows_b].cpu(), s["load"])
+                assert torch.equal(fin[g.rows_b].bool().cpu(), s["finished"])
+        cnt.zero_()
+        engine.env_step(g.kind, batch.demand, tours[:, :, t].to(torch.int32).contiguous(),
+                        load if g.kind == "cvrp" else None, vis, msk, fin if g.kind == "cvrp" else None, ninf, cnt)
+        if g.kind == "cvrp":
+            assert (int(cnt.item()) == 0) == (t == T - 1)
+
+
+@pytest.mark.parametrize("name", ["cvrp_n20", "cvrp_lib", "tsp_n20", "tsp_lib", "tsp_n30_m10"])
+def test_stepwise_api_equals_fused(name):
+    """Driving the drop-in classes step by step (the reference's protocol) gives the same tours as the
+    fused one-launch rollout: both run the same device code."""
+    import random
+    g = Golden(name)
+    if g.kind == "cvrp":
+        from elg_b200.cvrp import CVRPEnv as Env, CVRPModel as Model, rollout
+    else:
+        from elg_b200.tsp import TSPEnv as Env, TSPModel as Model, rollout
+    model = Model(**g.model_params())
+    model.decoder.add_local_policy(DEV)
+    model.load_state_dict(g.state_dict())
+    model = model.to(DEV)
+    env = Env(g.M, DEV)
+    z = g.z
+    if g.kind == "cvrp":
+        if g.meta.get("lib"):
+            env.load_vrplib_problem({"node_coord": z["lib_node_coord"], "demand": z["lib_demand"],
+                                     "capacity": int(z["lib_capacity"]), "depot": np.array([0])}, g.aug)
+        else:
+            env.load_random_problems({k: torch.tensor(z[k]) for k in ("depot", "loc", "demand")}, g.aug)
+    else:
+        if g.meta.get("lib"):
+            c = z["lib_node_coord"]
+            pts = (c - np.min(c)) / (np.max(c) - np.min(c))
+            env.load_tsplib_problem(torch.tensor(pts, dtype=torch.float)[None].to(DEV),
+                                    torch.tensor(c, dtype=torch.float)[None], g.aug)
+        else:
+            env.load_random_problems(torch.tensor(z["problems"]), g.aug)
+    out = {}
+    for fused in (True, False):
+        random.seed(g.meta["seed"])
+        reset_state, _, _ = env.reset()
+        model.pre_forward(reset_state)
+        model._elg_fused = fused
+        out[fused] = rollout(model, env, "greedy")
+    model._elg_fused = True
+    (t1, p1, r1), (t0, p0, r0) = out[True], out[False]
+    assert p1 is None and p0 is None
+    assert torch.equal(t1, t0)
+    assert (r1 - r0).abs().max() < 1e-5 * max(1.0, float(r0.abs().max()))
+    frac, _ = compare_tours(t1.cpu(), g.tours())
+    assert frac >= 0.97
+    assert t1.dtype == torch.int64 and t1.shape == (env.batch_size, g.M, t1.shape[2])
+
+
+def test_load_problems_bit_exact():
+    from elg_b200 import engine
+    from elg_b200.synth import synthetic_cvrp_batch, synthetic_tsp_batch
+    b = synthetic_cvrp_batch(5, 33, seed=3)
+    for aug in (1, 8):
+        ref = O.load_cvrp(b["depot"], b["loc"], b["demand"], aug)
+        xy, dem = engine.load_problems("cvrp", b["loc"].to(DEV), b["depot"].to(DEV), b["demand"].to(DEV), aug)
+        assert torch.equal(xy.cpu(), ref.xy) and torch.equal(dem.cpu(), ref.demand)
+        d = engine.pairwise_dist(xy).cpu()
+        assert (d == ref.dist).float().mean() > 0.98 and (d - ref.dist).abs().max() < 2e-7
+        p = synthetic_tsp_batch(4, 21, seed=aug)
+        xy, _ = engine.load_problems("tsp", p.to(DEV), aug=aug)
+        assert torch.equal(xy.cpu(), O.load_tsp(p, aug).xy)
+    with pytest.raises(NotImplementedError):
+        engine.load_problems("tsp", p.to(DEV), aug=3)
+
+
+@pytest.mark.parametrize("kind,N,M,n", [("cvrp", 100, 100, 6), ("tsp", 100, 100, 6), ("cvrp", 63, 37, 3), ("tsp", 77, 77, 2)])
+def test_fresh_instances_against_oracle(kind, N, M, n):
+    """Fresh seeded instances (not fixtures): fused CUDA rollout vs the fp32 oracle rollout on CPU."""
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    sd = synthetic_state_dict(kind, seed=4242, gain=4.0)
+    W = O.Weights(sd, kind, mp)
+    if kind == "cvrp":
+        b = synthetic_cvrp_batch(n, N, seed=N + M)
+        prob = O.load_cvrp(b["depot"], b["loc"], b["demand"], 8)
+    else:
+        prob = O.load_tsp(synthetic_tsp_batch(n, N, seed=N + M), 8)
+    perm = O.start_permutation(kind, N, M, seed=5)
+    ref_t, _, ref_r = O.rollout(W, prob, M, perm, "greedy")
+    handle = engine.ModelHandle(kind, mp, sd, DEV)
+    batch = engine.encode(handle, prob.xy.to(DEV), None if prob.demand is None else prob.demand.to(DEV))
+    tours16, reward, _, n_steps = engine.rollout(batch, M, perm.tolist())
+    T = int(n_steps.max())
+    tours = tours16[:, :, :T].long().cpu()
+    frac, same = compare_tours(tours, ref_t)
+    assert frac >= 0.95, frac
+    assert ((reward.cpu() - ref_r).abs() / ref_r.abs())[same].max() < 1e-4
+    _, got = O.best_of(reward.cpu(), 8, n)
+    _, want = O.best_of(ref_r, 8, n)
+    assert ((got - want).abs() / want).max() < 5e-3
+    if kind == "cvrp":
+        O.check_feasible_cvrp(tours, prob.demand)
+
+
+def test_sampling_mode_is_feasible_and_reproducible():
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
+    mp = dict(DEFAULT_MODEL_PARAMS["cvrp"])
+    sd = synthetic_state_dict("cvrp", seed=9, gain=2.0)
+    b = synthetic_cvrp_batch(4, 50, seed=8)
+    prob = O.load_cvrp(b["depot"], b["loc"], b["demand"], 1)
+    handle = engine.ModelHandle("cvrp", mp, sd, DEV)
+    batch = engine.encode(handle, prob.xy.to(DEV), prob.demand.to(DEV))
+    perm = O.start_permutation("cvrp", 50, 50, seed=1).tolist()
+    a = engine.rollout(batch, 50, perm, mode="sample", seed=123)
+    b2 = engine.rollout(batch, 50, perm, mode="sample", seed=123)
+    c = engine.rollout(batch, 50, perm, mode="sample", seed=124)
+    assert torch.equal(a[0], b2[0]) and torch.equal(a[2], b2[2])
+    assert not torch.equal(a[0], c[0])
+    T = int(a[3].max())
+    O.check_feasible_cvrp(a[0][:, :, :T].long().cpu(), prob.demand)
+    assert torch.isfinite(a[2]).all() and (a[2] < 0).all()
