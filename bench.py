@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the ELG rollout hot path: CVRP100 ELG-POMO greedy multi-start inference,
+POMO = 100, x8 augmentation, synthetic uniform instances, seeded random-init weights
+(BASELINE.json configs[1]; the released checkpoints are not available offline).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+                                                             # (CPU oracle port; the reference is Python
+                                                             # and cannot travel to the GPU box)
+
+A "step" is one evaluation batch through the reference's test() loop body: load + x8 augmentation,
+encoder, the whole greedy rollout, best-of-POMO and best-of-augmentation.  `value` = instances/s
+with the instances already resident in HBM; `e2e` = the same call fed from pinned HOST buffers
+with the H2D copy of the instances and the D2H copy of rewards/costs inside the timed region.
+Every step uses fresh instances; one batch's decoder tables are ~2 GB, far larger than L2.
+Rank layout (N > 1): one process per GPU, instances sharded across ranks, no data-path collective;
+time = max over ranks of the CUDA-event time, bracketed by barrier + synchronize.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES, POMO, AUG = 100, 100, 8
+WEIGHT_SEED, INSTANCE_SEED = 1234, 1234
+ALG_BYTES_PER_AUG_STEP = 161548        # K+V+enc re-read + node statics + row state, CVRP100
+ALG_FLOP_PER_ROW_STEP = 329088         # reference arithmetic per decode row-step, CVRP100
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_instances(n, seed):
+    from elg_b200.synth import synthetic_cvrp_batch
+    return synthetic_cvrp_batch(n, N_NODES, seed=seed)
+
+
+# ------------------------------------------------------------------------------------------- CPU arms
+def cpu_rollout_rate(n_inst, seed, threads=None):
+    """Reference algorithm on the host (oracle port, torch CPU): instances/s for one batch of n_inst."""
+    import torch
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
+    from oracle import elg_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    W = O.Weights(synthetic_state_dict("cvrp", seed=WEIGHT_SEED), "cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]))
+    data = make_instances(n_inst, seed)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], AUG)
+        perm = O.start_permutation("cvrp", N_NODES, POMO, seed=seed)
+        tours, _, reward = O.rollout(W, prob, POMO, perm, "greedy")
+        O.best_of(reward, AUG, n_inst)
+    dt = time.perf_counter() - t0
+    return n_inst / dt, dt, int(tours.shape[2])
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path, timed on host cores."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    n = args.ref_batch
+    times, T = [], 0
+    for s in range(args.warmup + args.steps):
+        rate, dt, T = cpu_rollout_rate(n, INSTANCE_SEED + s)
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {"impl": "reference", "metric": "CVRP100 instances/s (POMO x8 aug, greedy)", "value": value, "unit": "instances/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "ms_per_decode_step": 1e3 * total / len(times) / max(T, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n, 1),
+            "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port",
+                             "sample": "%d CVRP100 instances per step (x8 aug x 100 POMO rows), %d steps" % (n, args.steps)},
+            "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host_cpu_count": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch_per_gpu, n_gpus):
+    return {"workload": "CVRP100 ELG-POMO greedy multi-start inference, POMO=100, x8 augmentation, synthetic uniform instances",
+            "problem_size": N_NODES, "pomo": POMO, "aug": AUG, "instances_per_step_per_gpu": batch_per_gpu,
+            "weights": "seeded random init (released checkpoint not available offline)",
+            "l2_policy": "fresh instances every step; per-step decoder tables (~2 GB) exceed L2",
+            "parallelism": "instances sharded across %d GPU(s), no data-path collective" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from elg_b200 import _lib, engine
+    from elg_b200.cvrp import CVRPEnv, CVRPModel
+    from elg_b200.cvrp.test import solve_batch
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    mp = dict(DEFAULT_MODEL_PARAMS["cvrp"])
+    model = CVRPModel(**mp)
+    model.decoder.add_local_policy(dev)
+    model.load_state_dict(synthetic_state_dict("cvrp", seed=WEIGHT_SEED))
+    model = model.to(dev).eval().requires_grad_(False)
+    env = CVRPEnv(POMO, dev)
+    nb = args.batch
+    total_steps = args.warmup + args.steps
+
+    # synthetic instances: every (step, rank) gets its own seeded batch; host copies are pinned
+    host = []
+    for s in range(total_steps):
+        d = make_instances(nb, INSTANCE_SEED + 7919 * s + rank)
+        host.append({k: v.pin_memory() for k, v in d.items()})
+    dev_batches = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    out_host = {"costs": torch.empty((2, nb), dtype=torch.float32).pin_memory(),
+                "rewards": torch.empty((AUG * nb, POMO), dtype=torch.float32).pin_memory()}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device(s):
+        random.seed(INSTANCE_SEED + s)
+        return solve_batch(model, env, dev_batches[s], AUG)
+
+    def step_e2e(s):
+        random.seed(INSTANCE_SEED + s)
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host[s].items()}
+        no_aug, aug, _, rewards = solve_batch(model, env, batch, AUG)
+        out_host["costs"][0].copy_(no_aug, non_blocking=True)
+        out_host["costs"][1].copy_(aug, non_blocking=True)
+        out_host["rewards"].copy_(rewards, non_blocking=True)
+        return no_aug, aug
+
+    def timed(fn):
+        for s in range(args.warmup):
+            fn(s)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        engine.profile_events = []
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        costs = []
+        for s in range(args.warmup, total_steps):
+            costs.append(fn(s)[1].mean())
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = _lib.launch_count() - launches0
+        events, engine.profile_events = engine.profile_events, None
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, events, clocks, float(torch.stack(costs).mean())
+
+    ms_dev, launches, events, clocks, mean_cost = timed(step_device)
+    ms_e2e, _, _, clocks_e2e, _ = timed(step_e2e)
+
+    # rollout-kernel roofline numbers from the CUDA events recorded around each elg_rollout launch
+    k_ms, aug_steps, row_steps, T_list = 0.0, 0, 0, []
+    for e0, e1, n_steps, tiles in events:
+        k_ms += e0.elapsed_time(e1)
+        per_inst = n_steps.view(-1, tiles).max(dim=1)[0]
+        aug_steps += int(per_inst.sum())
+        row_steps += int(per_inst.sum()) * POMO
+        T_list.append(int(n_steps.max()))
+    peaks, peak_src = measured_peaks()
+    ach_gbs = ALG_BYTES_PER_AUG_STEP * aug_steps / (k_ms * 1e-3) / 1e9
+    ach_tf = ALG_FLOP_PER_ROW_STEP * row_steps / (k_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        n_total = nb * world * args.steps
+        value = n_total / (ms_dev * 1e-3)
+        e2e = n_total / (ms_e2e * 1e-3)
+        line = {
+            "metric": "CVRP100 instances/s (POMO x8 aug, greedy)", "value": value, "unit": "instances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "ms_per_decode_step": k_ms / max(sum(T_list), 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(nb, world),
+            "e2e": {"value": e2e, "unit": "instances/s", "h2d_bytes_per_step": nb * (2 + 2 * N_NODES + N_NODES) * 4,
+                    "d2h_bytes_per_step": 2 * nb * 4 + AUG * nb * POMO * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks, "clocks_e2e": clocks_e2e,
+            "roofline": {"kernel": "rollout_kernel<CVRP> (decode step + env step, whole rollout in one launch)",
+                         "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_aug_instance_step": ALG_BYTES_PER_AUG_STEP,
+                         "aug_instance_steps_per_launch": aug_steps / max(len(events), 1),
+                         "kernel_ms_per_launch": k_ms / max(len(events), 1),
+                         "kernel_share_of_step": k_ms / ms_dev,
+                         "note": "K/V/E' stay resident in shared memory for the whole rollout, so the streaming-model "
+                                 "HBM bytes are (by design) not moved; the binding unit is the fp32 FMA pipe, see fp32"},
+            "fp32": {"achieved": ach_tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FP32_PEAK_TFLOPS,
+                     "flop_per_row_step": ALG_FLOP_PER_ROW_STEP,
+                     "note": "reference-arithmetic FLOPs (SURVEY 8d) / rollout-kernel time; peak = 148 SM x 128 FMA x 2 x 1.965 GHz"},
+            "mean_aug_cost": mean_cost, "rollout_steps_T": T_list,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt, T = cpu_rollout_rate(args.cpu_sample, INSTANCE_SEED)
+            line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "%d CVRP100 instances (x8 aug x 100 POMO rows), one batch, %.1f s, T=%d; "
+                                              "oracle port of the reference's torch-CPU path" % (args.cpu_sample, dt, T),
+                                    "host_cpu_count": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1000, help="instances per step per GPU (10 steps = the 10k-instance config)")
+    ap.add_argument("--ref-batch", type=int, default=8, help="instances per step for --impl reference (bounded sample)")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="instances in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not os.environ.get("ELG_BENCH_ALLOW_SHORT"):
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

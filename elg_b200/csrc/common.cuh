@@ -21,7 +21,7 @@ constexpr int KT_MAX = 64;  // max local sequence length (local_k + depot)
 constexpr int DER_WQN = 0;                    // [E][E]  node part of Wq_last
 constexpr int DER_WL = DER_WQN + E * E;       // [E]     load column of Wq_last (cvrp) / zeros
 constexpr int DER_WQF = DER_WL + E;           // [E][E]  Wq_first (tsp) / zeros
-constexpr int DER_WK4 = DER_WQF + E * E;      // [E][E]  Wk / sqrt(D)
+constexpr int DER_WK4 = DER_WQF + E * E;      // [E][E]  Wk * log2(e) / sqrt(D)
 constexpr int DER_WET = DER_WK4 + E * E;      // [E][E]  WET[i][k] = Wo[k][i] / sqrt(E)
 constexpr int DER_BE = DER_WET + E * E;       // [E]     bo / sqrt(E)
 constexpr int DER_LOC = DER_BE + E;           // local-policy tables

@@ -46,7 +46,7 @@ __global__ void prepare_kernel(elg_model_desc d, elg_weight_layout_t L, const fl
     int o = i / E, c = i % E;
     der[DER_WQN + i] = w[L.dec_wq_last + (int64_t)o * ldq + c];
     der[DER_WQF + i] = cvrp ? 0.f : w[L.dec_wq_first + i];
-    der[DER_WK4 + i] = w[L.dec_wk + i] * 0.25f;
+    der[DER_WK4 + i] = w[L.dec_wk + i] * 0.36067376022224085f;   // log2(e) / sqrt(D): phase A works in the log2 domain
     der[DER_WET + i] = w[L.dec_wo + (int64_t)c * E + o] / inv_sqrt_e;   // WET[o=i][c=k] = Wo[k][i]/sqrt(E)
   }
   for (int i = tid; i < E; i += nt) {

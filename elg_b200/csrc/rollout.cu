@@ -318,37 +318,52 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           float m = -INFINITY, l = 0.f;
           const float* kp = sK + h * D;
           const float* vp = sV + h * D;
-          for (int j = 0; j < N1; ++j) {
-            const uint32_t mw = j < 32 ? mw0 : (j < 64 ? mw1 : (j < 96 ? mw2 : mw3));
-            const bool use = !((mw >> (j & 31)) & 1u);
-            if (!__any_sync(FULL, use)) continue;
+          // K is pre-scaled by log2(e)/sqrt(D): scores live in the log2 domain, weights are 2^(s-m).
+          // Only nodes that at least one lane of the warp still needs are visited (warp-uniform loop).
+          auto key = [&](const int j, const bool use) {
             const float4* kr = reinterpret_cast<const float4*>(kp + j * E);
             float s = 0.f;
 #pragma unroll
             for (int d4 = 0; d4 < D / 4; ++d4) {
-              float4 kk = kr[d4];
+              const float4 kk = kr[d4];
               s = fmaf(q[d4 * 4], kk.x, s); s = fmaf(q[d4 * 4 + 1], kk.y, s);
               s = fmaf(q[d4 * 4 + 2], kk.z, s); s = fmaf(q[d4 * 4 + 3], kk.w, s);
             }
             if (use) {
-              if (s > m + 8.f) {          // lazy rescale of the running softmax reference
-                const float c = expf(m - s);
+              if (s > m + 12.f) {          // lazy rescale of the running softmax reference
+                const float c = exp2f(m - s);
                 l *= c;
 #pragma unroll
                 for (int d = 0; d < D; ++d) o[d] *= c;
                 m = s;
               }
-              const float p = expf(s - m);
+              const float p = exp2f(s - m);
               l += p;
               const float4* vr = reinterpret_cast<const float4*>(vp + j * E);
 #pragma unroll
               for (int d4 = 0; d4 < D / 4; ++d4) {
-                float4 vv = vr[d4];
+                const float4 vv = vr[d4];
                 o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
                 o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
               }
             }
+          };
+#define ELG_KEY_WORD(W, MW)                                                              \
+          {                                                                                \
+            const int nb = N1 - (W) * 32;                                                  \
+            const uint32_t lim = nb >= 32 ? FULL : (nb <= 0 ? 0u : ((1u << nb) - 1u));     \
+            uint32_t bits = __reduce_or_sync(FULL, ~(MW)) & lim;                           \
+            while (bits) {                                                                 \
+              const int jb = __ffs(bits) - 1;                                              \
+              bits &= bits - 1;                                                            \
+              key((W) * 32 + jb, !(((MW) >> jb) & 1u));                                    \
+            }                                                                              \
           }
+          ELG_KEY_WORD(0, mw0)
+          ELG_KEY_WORD(1, mw1)
+          ELG_KEY_WORD(2, mw2)
+          ELG_KEY_WORD(3, mw3)
+#undef ELG_KEY_WORD
           if (act) {
             const float inv = 1.f / l;
             float4* op = reinterpret_cast<float4*>(sO + r * E + h * D);

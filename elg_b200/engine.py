@@ -174,6 +174,10 @@ def encode(handle, xy, demand=None, unscaled=None):
     return batch
 
 
+# when set to a list, rollout() appends (start_event, end_event, n_steps tensor) around the kernel launch
+profile_events = None
+
+
 def rollout(batch, M, start_nodes, mode="greedy", seed=0, sync_tours=True):
     """Whole construction rollout in one launch.
 
@@ -193,10 +197,16 @@ def rollout(batch, M, start_nodes, mode="greedy", seed=0, sync_tours=True):
     n_steps = torch.zeros(B * tiles + 1, dtype=torch.int32, device=dev)      # last slot = work counter
     logp = torch.empty((B, M), dtype=torch.float32, device=dev) if mode == "sample" else None
     with torch.cuda.device(dev):
+        if profile_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(dev))
         check(lib.elg_rollout(h.desc, _ptr(h.derived), batch.tables, B, M, N1, _ptr(start),
                               ELG_SAMPLE if mode == "sample" else ELG_GREEDY, int(seed) & (2 ** 64 - 1), t_max,
                               _ptr(tours), _ptr(reward), _ptr(n_steps), _ptr(logp),
                               C.c_void_p(n_steps.data_ptr() + 4 * B * tiles), _stream(dev)))
+        if profile_events is not None:
+            ev1.record(torch.cuda.current_stream(dev))
+            profile_events.append((ev0, ev1, n_steps[:B * tiles], tiles))
     return tours, reward, logp, n_steps[:B * tiles]
 
 

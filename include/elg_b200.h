@@ -96,7 +96,7 @@ typedef struct elg_tables {
   const float* demand;    /* [B][N1]      cvrp (demand[.,0] = 0); NULL for tsp                   */
   const float* unscaled;  /* [B][N1][2]   library instances: unscaled coordinates, else NULL     */
   float* enc;             /* [B][N1][E]   encoded nodes                                          */
-  float* k;               /* [B][N1][E]   decoder keys, pre-scaled by 1/sqrt(qkv)                */
+  float* k;               /* [B][N1][E]   decoder keys, pre-scaled by log2(e)/sqrt(qkv)          */
   float* v;               /* [B][N1][E]   decoder values                                         */
   float* e;               /* [B][N1][E]   score matrix  E' = enc * Wo^T-fold / sqrt(E), swizzled */
   float* eb;              /* [B][N1]      score bias    enc . bo / sqrt(E)                       */

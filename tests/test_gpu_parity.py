@@ -57,7 +57,7 @@ def test_teacher_forced_logits_and_choices(case):
                                             want_logits=True)
         logits, sel = logits.cpu(), sel.cpu()
         ref = s["logits"]
-        live = torch.ones(ref.shape[:2], dtype=torch.bool) if g.kind == "tsp" else ~s["finished"]
+        live = torch.ones(ref.shape[:2], dtype=torch.bool)      # decode_step evaluates every row, finished or not
         assert torch.equal(torch.isinf(logits)[live], torch.isinf(ref)[live])
         fin = ~torch.isinf(ref) & live[:, :, None]
         err = (logits[fin] - ref[fin]).abs()
@@ -98,7 +98,8 @@ def test_fused_rollout_matches_reference_tours(case):
         xy = prob.unscaled_xy.expand(batch.B, -1, -1) if g.kind == "tsp" else prob.unscaled_xy
         assert torch.equal(-O.tour_length(xy, tours, rounding=True), reward.cpu())
     else:
-        assert (O.tour_length(prob.xy, tours) + reward.cpu()).abs().max() < 2e-5
+        own = O.tour_length(prob.xy, tours)          # torch sums pairwise, the kernel sequentially
+        assert ((own + reward.cpu()).abs() / own).max() < 5e-6
     # best-of-POMO / best-of-aug cost agrees with the reference's
     if g.aug == 8:
         n = batch.B // 8
