@@ -18,7 +18,7 @@
 
 namespace elg {
 
-int launch_neighbours(int problem, const float* xy, int B, int N1, uint8_t* nbr, cudaStream_t stream);
+int launch_neighbours(int problem, const float* xy, int B, int N1, void* nbr, cudaStream_t stream);
 
 // ---- embedding --------------------------------------------------------------------------------
 __global__ void embed_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand,
@@ -324,7 +324,7 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
     ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQF, t->qfirst, nullptr, nullptr, rows, E, E, E, N1, st));
   row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
   ELG_LAUNCH_OK();
-  if (t->nbr && N1 <= ELG_MAX_NODES_RESIDENT) ELG_TRY(launch_neighbours(d->problem, t->xy, B, N1, t->nbr, st));
+  if (t->nbr) ELG_TRY(launch_neighbours(d->problem, t->xy, B, N1, t->nbr, st));
   return ELG_OK;
 }
 

@@ -61,7 +61,7 @@ __global__ void pairwise_dist_kernel(const float* __restrict__ xy, int B, int N1
 // which is what torch.topk(k, largest=False) over the masked distance row yields in the reference
 // (CVRP/models.py:74,375; TSP/models.py:62,286) -- computed once instead of twice per step.
 __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int N1, uint8_t* __restrict__ nbr) {
-  __shared__ float sd[ELG_MAX_NODES_RESIDENT];
+  __shared__ float sd[128];
   const int i = blockIdx.x % N1, b = blockIdx.x / N1;
   const float* p = xy + (size_t)b * N1 * 2;
   const int j0 = problem == ELG_CVRP ? 1 : 0;
@@ -81,7 +81,44 @@ __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int 
   }
 }
 
-// ---- environment step on bit masks (one warp per row) -----------------------------------------
+// ---- neighbour lists for the streaming variant (N1 > 112): uint16 ids, linear order ------------------
+// One CTA per (aug-instance, node): bitonic sort of (distance bits << 32 | index) keys in shared memory.
+__global__ void __launch_bounds__(512) neighbour_sort_kernel(int problem, const float* __restrict__ xy, int N1,
+                                                             uint16_t* __restrict__ out, int stride, int P) {
+  extern __shared__ unsigned long long skeys[];
+  const int i = blockIdx.x % N1, b = blockIdx.x / N1;
+  const float* p = xy + (size_t)b * N1 * 2;
+  const int j0 = problem == ELG_CVRP ? 1 : 0;
+  const int NL = N1 - j0;
+  const float xi = p[2 * i], yi = p[2 * i + 1];
+  for (int e = threadIdx.x; e < P; e += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (e < NL) {
+      const int j = e + j0;
+      const float d = dist2(xi - p[2 * j], yi - p[2 * j + 1]);
+      key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+    }
+    skeys[e] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int e = threadIdx.x; e < P; e += blockDim.x) {
+        const int partner = e ^ j;
+        if (partner > e) {
+          const unsigned long long a = skeys[e], c = skeys[partner];
+          const bool up = (e & k) == 0;
+          if ((a > c) == up) { skeys[e] = c; skeys[partner] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  uint16_t* row = out + ((size_t)b * N1 + i) * stride;
+  for (int e = threadIdx.x; e < stride; e += blockDim.x) row[e] = e < NL ? (uint16_t)(skeys[e] & 0xffffu) : (uint16_t)0;
+}
+
+// ---- environment step on bit masks (one warp per row, W = ceil(N1/32) words per row) ----------------
 // reference: CVRPEnv.step (CVRP/CVRPEnv.py:190-249), TSPEnv.step (TSP/TSPEnv.py:108-133)
 __global__ void env_step_kernel(int problem, const float* __restrict__ demand, int B, int M, int N1,
                                 const int32_t* __restrict__ selected, float* __restrict__ load,
@@ -91,41 +128,45 @@ __global__ void env_step_kernel(int problem, const float* __restrict__ demand, i
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= (long long)B * M) return;
+  const int W = (N1 + 31) >> 5;
   const int b = (int)(row / M);
   const int sel = selected[row];
-  uint32_t vis[4], msk[4];
-#pragma unroll
-  for (int w = 0; w < 4; ++w) vis[w] = visited[row * 4 + w];
-  vis[sel >> 5] |= 1u << (sel & 31);
+  uint32_t* vis = visited + row * W;
+  uint32_t* msk = mask + row * W;
   bool fin = false;
   if (problem == ELG_CVRP) {
     const float* dem = demand + (size_t)b * N1;
     const bool at_depot = sel == 0;
     float ld = load[row];
     ld = at_depot ? 1.f : ld - dem[sel];
-    if (at_depot) vis[0] |= 1u; else vis[0] &= ~1u;
     bool all_vis = true;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      int j = w * 32 + lane;
-      bool big = j < N1 && (__fadd_rn(ld, 1e-6f) < dem[j]);
-      uint32_t bw = __ballot_sync(0xffffffffu, big);
-      msk[w] = vis[w] | bw;
-      int nb = N1 - w * 32;
-      uint32_t full = nb >= 32 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
-      all_vis = all_vis && ((vis[w] & full) == full);
+    for (int w = 0; w < W; ++w) {
+      uint32_t vw = vis[w];
+      if (w == (sel >> 5)) vw |= 1u << (sel & 31);
+      if (w == 0) vw = at_depot ? (vw | 1u) : (vw & ~1u);
+      const int j = w * 32 + lane;
+      const uint32_t big = __ballot_sync(0xffffffffu, j < N1 && (__fadd_rn(ld, 1e-6f) < dem[min(j, N1 - 1)]));
+      const int nb = N1 - w * 32;
+      const uint32_t full = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+      all_vis = all_vis && ((vw & full) == full);
+      __syncwarp();
+      if (lane == 0) { vis[w] = vw; msk[w] = vw | big; }
     }
     fin = finished[row] || all_vis;
-    if (fin) msk[0] &= ~1u;
-    if (lane == 0) { load[row] = ld; finished[row] = fin ? 1 : 0; }
+    __syncwarp();
+    if (lane == 0) {
+      if (fin) msk[0] &= ~1u;
+      load[row] = ld;
+      finished[row] = fin ? 1 : 0;
+    }
   } else {
-#pragma unroll
-    for (int w = 0; w < 4; ++w) msk[w] = vis[w];
+    if (lane == 0) {
+      const uint32_t vw = vis[sel >> 5] | (1u << (sel & 31));
+      vis[sel >> 5] = vw;
+      msk[sel >> 5] = vw;
+    }
   }
-  if (lane < 4) {
-    visited[row * 4 + lane] = vis[lane];
-    mask[row * 4 + lane] = msk[lane];
-  }
+  __syncwarp();
   if (ninf_mask) {
     for (int j = lane; j < N1; j += 32)
       ninf_mask[row * N1 + j] = ((msk[j >> 5] >> (j & 31)) & 1u) ? -INFINITY : 0.f;
@@ -204,6 +245,13 @@ int elg_load_problems(int problem, const float* depot_xy, const float* node_xy, 
   return ELG_OK;
 }
 
+size_t elg_nbr_bytes(int problem, int B, int N1) {
+  if (B <= 0 || N1 <= 1) return 0;
+  if (N1 <= ELG_MAX_NODES_RESIDENT) return (size_t)B * N1 * ELG_NBR_STRIDE;
+  const int NL = N1 - (problem == ELG_CVRP ? 1 : 0);
+  return (size_t)B * N1 * ELG_NBR16_STRIDE(NL) * sizeof(uint16_t);
+}
+
 int elg_pairwise_dist(const float* xy, int B, int N1, float* dist_out, void* stream) {
   ELG_REQUIRE(xy && dist_out && B > 0 && N1 > 0, ELG_EINVAL, "bad sizes/pointers");
   pairwise_dist_kernel<<<grid_for((long long)B * N1 * N1, 256), 256, 0, (cudaStream_t)stream>>>(xy, B, N1, dist_out);
@@ -215,7 +263,7 @@ int elg_env_step(int problem, const float* demand, int B, int M, int N1, const i
                  uint32_t* visited_bits, uint32_t* mask_bits, uint8_t* finished, float* ninf_mask,
                  int32_t* n_unfinished, void* stream) {
   ELG_REQUIRE(problem == ELG_TSP || problem == ELG_CVRP, ELG_EINVAL, "unknown problem %d", problem);
-  ELG_REQUIRE(N1 > 0 && N1 <= 128, ELG_EUNSUPPORTED, "bit-mask env supports up to 128 nodes (got %d)", N1);
+  ELG_REQUIRE(N1 > 0, ELG_EINVAL, "bad node count %d", N1);
   ELG_REQUIRE(selected && visited_bits && mask_bits, ELG_EINVAL, "NULL state pointer");
   ELG_REQUIRE(problem == ELG_TSP || (demand && load && finished), ELG_EINVAL, "cvrp needs demand/load/finished");
   long long threads = (long long)B * M * 32;
@@ -248,11 +296,25 @@ int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M
 
 }  // extern "C"
 
-// neighbour lists are built by elg_encode (encoder.cu) through this launcher
+// neighbour lists are built by elg_encode (encoder.cu) through this launcher:
+// resident variant (N1 <= 112): uint8 ids, 8-way interleaved, ELG_NBR_STRIDE bytes per node;
+// streaming variant: uint16 ids in rank order, ELG_NBR16_STRIDE(NL) entries per node.
 namespace elg {
-int launch_neighbours(int problem, const float* xy, int B, int N1, uint8_t* nbr, cudaStream_t stream) {
-  ELG_REQUIRE(N1 <= ELG_MAX_NODES_RESIDENT, ELG_EUNSUPPORTED, "neighbour lists support up to %d nodes", ELG_MAX_NODES_RESIDENT);
-  neighbour_kernel<<<(unsigned)B * N1, 128, 0, stream>>>(problem, xy, N1, nbr);
+bool rollout_is_resident(int N1);
+int launch_neighbours(int problem, const float* xy, int B, int N1, void* nbr, cudaStream_t stream) {
+  if (rollout_is_resident(N1)) {
+    neighbour_kernel<<<(unsigned)B * N1, 128, 0, stream>>>(problem, xy, N1, reinterpret_cast<uint8_t*>(nbr));
+    ELG_LAUNCH_OK();
+    return ELG_OK;
+  }
+  const int NL = N1 - (problem == ELG_CVRP ? 1 : 0);
+  ELG_REQUIRE(N1 <= 8192, ELG_EUNSUPPORTED, "neighbour lists support up to 8192 nodes (got %d)", N1);
+  int P = 64;
+  while (P < NL) P <<= 1;
+  const int stride = ELG_NBR16_STRIDE(NL);
+  const size_t smem = (size_t)P * sizeof(unsigned long long);
+  ELG_CUDA_OK(cudaFuncSetAttribute(neighbour_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  neighbour_sort_kernel<<<(unsigned)B * N1, 512, smem, stream>>>(problem, xy, N1, reinterpret_cast<uint16_t*>(nbr), stride, P);
   ELG_LAUNCH_OK();
   return ELG_OK;
 }

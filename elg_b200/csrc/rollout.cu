@@ -1,6 +1,6 @@
 // Persistent rollout kernel: the whole autoregressive construction loop of one aug-instance
 // (decode step of the global POMO attention policy + local k-nearest attention policy + env step)
-// runs inside one CTA, with the decoder keys/values/score matrix resident in shared memory.
+// runs inside one CTA.
 //
 // reference per-step path (file:line under the reference tree):
 //   rollout                      CVRP/utils.py:7-29            TSP/utils.py:7-26
@@ -13,15 +13,18 @@
 //
 // Work decomposition (DESIGN.md has the full story):
 //   CTA   = one (aug-instance, tile of <= 64 POMO rows), 16 warps, persistent over work items.
-//   smem  = K, V, E' of the instance (3 x N1 x 128 fp32, brought in by cp.async.bulk), the per-row
-//           attention outputs, the folded local-policy tables and the bit-mask row state.
-//   phase A  thread = (row, head): q . K over all unmasked nodes with a lazily rescaled online
-//            softmax and the weighted V sum; K/V rows are warp-broadcast shared-memory reads.
-//   phase B  warp = 4 rows: score tile (4 rows x 4 node-chunks per lane) against E'; then the local
-//            policy with an octet of lanes per row (neighbour walk over the presorted list,
-//            polar features, 4-head attention with the constant query folded into 3-vector dots);
-//            logits = clip*tanh(score + penalty + local) + mask; argmax or Philox sampling.
-//   phase C  env step on bit masks (load recurrence in fp32, visited/too-large masks, finished).
+//   RESIDENT (N1 <= 112): K', V, E' of the instance (3 x N1 x 128 fp32) are brought into shared
+//           memory once per work item by cp.async.bulk (TMA) and stay there for the whole rollout.
+//   STREAMING (N1 <= 8192): K', V, E' are read through L1/L2 every step (all warps of a CTA walk the
+//           nodes in the same order, so a line is fetched from L2 about once per CTA per step).
+//   phase A  thread = (row, head): q . K over the warp-union of unmasked nodes with a lazily rescaled
+//            online softmax (log2 domain) and the weighted V sum; K/V rows are warp-broadcast loads.
+//   phase B  warp = 4 rows.  B1: local policy with an octet of lanes per row (walk over the
+//            distance-presorted neighbour list, polar features, 4-head attention with the constant
+//            query folded into 3-vector dots + tables).  B2: score tile (4 rows x 4 node-chunks per
+//            lane) against E', 128 nodes at a time.  B3: clip*tanh(score + penalty + local) + mask,
+//            running first-max argmax (or Philox sampling when N1 <= 128).
+//   phase C  env step on bit masks (fp32 load recurrence, visited / too-large masks by warp ballots).
 #include <string.h>
 #include "common.cuh"
 
@@ -30,8 +33,9 @@ namespace elg {
 constexpr int RW = 16;              // warps per CTA
 constexpr int RT = RW * 32;         // threads per CTA
 constexpr int MT_MAX = 64;          // rows per CTA
-constexpr int N_RES_MAX = 112;      // nodes the resident kernel supports
-constexpr int DS = 112;             // stride of the per-row dense penalty+local scratch
+constexpr int N_RES_MAX = 112;      // nodes the resident variant supports
+constexpr int N_STREAM_MAX = 8192;  // nodes the streaming variant supports (uint16 ids, sort kernel)
+constexpr int DS = 128;             // stride of the per-row dense penalty+local scratch (one node chunk)
 constexpr int TS = 36;              // padded row stride of the VPE / PE tables in smem
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -64,20 +68,21 @@ struct RolloutArgs {
 // ---- shared-memory layout (offsets in floats) ---------------------------------------------------
 struct SmemLayout {
   int k, v, e, o, eb, xy, dem, wl, u, tt, a, cv, vpe, pe, wct, bc, we, be;
-  int cur, first, load, tlen, fin, logp, mask, vis, ctrl, bar;
+  int cur, first, load, tlen, fin, logp, mask, vis, ids, dense, ctrl, bar;
   int total;     // floats
 };
 __host__ __device__ inline int r4(int x) { return (x + 3) & ~3; }
-__host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT) {
+__host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT, bool resident) {
   SmemLayout L;
+  const int W = (N1 + 31) >> 5;
   int o = 0;
-  L.k = o; o += N1 * E;
-  L.v = o; o += N1 * E;
-  L.e = o; o += N1 * E;
+  L.k = o; o += resident ? N1 * E : 0;
+  L.v = o; o += resident ? N1 * E : 0;
+  L.e = o; o += resident ? N1 * E : 0;
   L.o = o; o += MT * E;
-  L.eb = o; o += r4(N1);
-  L.xy = o; o += r4(2 * N1);
-  L.dem = o; o += r4(N1);
+  L.eb = o; o += resident ? r4(N1) : 0;
+  L.xy = o; o += resident ? r4(2 * N1) : 0;
+  L.dem = o; o += resident ? r4(N1) : 0;
   L.wl = o; o += E;
   L.u = o; o += LH * 4;
   L.tt = o; o += LH * KT_MAX;
@@ -95,8 +100,10 @@ __host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT) {
   L.tlen = o; o += MT;
   L.fin = o; o += MT;
   L.logp = o; o += MT;
-  L.mask = o; o += MT * 4;
-  L.vis = o; o += MT * 4;
+  L.mask = o; o += r4(MT * W);
+  L.vis = o; o += r4(MT * W);
+  L.ids = o; o += RW * 4 * (KT_MAX / 2);            // per warp: 4 rows x 64 uint16 neighbour ids
+  L.dense = o; o += resident ? 0 : RW * 4 * DS;     // resident: aliases the warp's dead attention rows
   L.ctrl = o; o += 4;
   L.bar = o; o += 4;
   L.total = o;
@@ -151,21 +158,16 @@ __device__ __forceinline__ float octet_sum(float v) {
 }
 
 // =================================================================================================
-template <int PROBLEM, int MAXE>
+template <int PROBLEM, int MAXE, bool RESIDENT>
 __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
   constexpr bool CVRP = PROBLEM == ELG_CVRP;
   constexpr int DEP = CVRP ? 1 : 0;
   extern __shared__ __align__(128) float sm[];
   const int N1 = A.N1;
+  const int W = (N1 + 31) >> 5;                  // mask words per row
   const int KT = MAXE * 8;
-  const SmemLayout L = make_layout(N1, A.MT, KT);
-  float* sK = sm + L.k;
-  float* sV = sm + L.v;
-  float* sE = sm + L.e;
+  const SmemLayout L = make_layout(N1, A.MT, KT, RESIDENT);
   float* sO = sm + L.o;
-  float* sEb = sm + L.eb;
-  float* sXY = sm + L.xy;
-  float* sDem = sm + L.dem;
   float* sWL = sm + L.wl;
   const float* sU = sm + L.u;
   const float* sT = sm + L.tt;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
       w[L.pe + p * TS + c] = loc[LOC_PE + i];
     }
     for (int i = tid; i < LE * LE; i += RT) w[L.wct + i] = loc[LOC_WCT + i];
-    if (tid == 0) {
+    if (RESIDENT && tid == 0) {
       mbar_init(bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 
   const int total_work = A.B * A.tiles;
   uint32_t bar_phase = 0;
-  const float inv_sqrt_le = 5.656854249492381f;   // sqrt(32), used as a divisor like the reference
+  const float sqrt_le = 5.656854249492381f;   // sqrt(32), used as a divisor like the reference
 
   for (int iter = 0;; ++iter) {
     // ---- fetch work: dynamic (atomic counter) for rollouts, static for single decode steps ------
@@ -231,20 +233,30 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
     const int row0 = tile * A.MT;
     const int nrows = min(A.MT, A.M - row0);
 
-    // ---- stage the instance: K, V, E' by TMA bulk copies; small vectors by plain loads ---------
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)N1 * E * sizeof(float);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, 3 * bytes);
-      bulk_g2s(sK, A.t.k + (size_t)b * N1 * E, bytes, bar);
-      bulk_g2s(sV, A.t.v + (size_t)b * N1 * E, bytes, bar);
-      bulk_g2s(sE, A.t.e + (size_t)b * N1 * E, bytes, bar);
-    }
-    for (int i = tid; i < N1; i += RT) {
-      sEb[i] = A.t.eb[(size_t)b * N1 + i];
-      sXY[2 * i] = A.t.xy[((size_t)b * N1 + i) * 2];
-      sXY[2 * i + 1] = A.t.xy[((size_t)b * N1 + i) * 2 + 1];
-      sDem[i] = CVRP ? A.t.demand[(size_t)b * N1 + i] : 0.f;
+    // ---- the instance's tables: shared memory (resident) or global memory through L1/L2 ---------
+    const float *pK, *pV, *pE, *pEb, *pXY, *pDem;
+    if (RESIDENT) {
+      float* sK = sm + L.k; float* sV = sm + L.v; float* sE = sm + L.e;
+      float* sEb = sm + L.eb; float* sXY = sm + L.xy; float* sDem = sm + L.dem;
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)N1 * E * sizeof(float);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, 3 * bytes);
+        bulk_g2s(sK, A.t.k + (size_t)b * N1 * E, bytes, bar);
+        bulk_g2s(sV, A.t.v + (size_t)b * N1 * E, bytes, bar);
+        bulk_g2s(sE, A.t.e + (size_t)b * N1 * E, bytes, bar);
+      }
+      for (int i = tid; i < N1; i += RT) {
+        sEb[i] = A.t.eb[(size_t)b * N1 + i];
+        sXY[2 * i] = A.t.xy[((size_t)b * N1 + i) * 2];
+        sXY[2 * i + 1] = A.t.xy[((size_t)b * N1 + i) * 2 + 1];
+        sDem[i] = CVRP ? A.t.demand[(size_t)b * N1 + i] : 0.f;
+      }
+      pK = sK; pV = sV; pE = sE; pEb = sEb; pXY = sXY; pDem = sDem;
+    } else {
+      pK = A.t.k + (size_t)b * N1 * E; pV = A.t.v + (size_t)b * N1 * E; pE = A.t.e + (size_t)b * N1 * E;
+      pEb = A.t.eb + (size_t)b * N1; pXY = A.t.xy + (size_t)b * N1 * 2;
+      pDem = CVRP ? A.t.demand + (size_t)b * N1 : A.t.eb;
     }
     for (int r = tid; r < A.MT; r += RT) {
       const size_t g = (size_t)b * A.M + row0 + r;
@@ -253,20 +265,23 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
         sCur[r] = A.st_cur[g];
         sFirst[r] = CVRP ? 0 : A.st_first[g];
         sLoad[r] = CVRP ? A.st_load[g] : 1.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { sMask[r * 4 + w] = A.st_mask[g * 4 + w]; sVis[r * 4 + w] = 0u; }
         sFin[r] = 0;
       } else {
         sCur[r] = 0; sFirst[r] = 0; sLoad[r] = 1.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { sMask[r * 4 + w] = 0u; sVis[r * 4 + w] = 0u; }
         sFin[r] = ok ? 0 : 1;
       }
       sTlen[r] = 0.f;
       sLogp[r] = 0.f;
     }
-    mbar_wait(bar, bar_phase);
-    bar_phase ^= 1;
+    for (int i = tid; i < A.MT * W; i += RT) {
+      const int r = i / W, w = i % W;
+      sVis[i] = 0u;
+      sMask[i] = (A.single_step && r < nrows) ? A.st_mask[((size_t)b * A.M + row0 + r) * W + w] : 0u;
+    }
+    if (RESIDENT) {
+      mbar_wait(bar, bar_phase);
+      bar_phase ^= 1;
+    }
     __syncthreads();
 
     // ---- the construction loop ----------------------------------------------------------------
@@ -290,7 +305,6 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           }
           act = act && !sFin[r];
           float q[D], o[D];
-          uint32_t mw0 = FULL, mw1 = FULL, mw2 = FULL, mw3 = FULL;
           if (act) {
             const int cur = sCur[r];
             const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + h * D);
@@ -308,7 +322,6 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
               }
               q[d4 * 4] = v4.x; q[d4 * 4 + 1] = v4.y; q[d4 * 4 + 2] = v4.z; q[d4 * 4 + 3] = v4.w;
             }
-            mw0 = sMask[r * 4]; mw1 = sMask[r * 4 + 1]; mw2 = sMask[r * 4 + 2]; mw3 = sMask[r * 4 + 3];
           } else {
 #pragma unroll
             for (int d = 0; d < D; ++d) q[d] = 0.f;
@@ -316,54 +329,47 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 #pragma unroll
           for (int d = 0; d < D; ++d) o[d] = 0.f;
           float m = -INFINITY, l = 0.f;
-          const float* kp = sK + h * D;
-          const float* vp = sV + h * D;
+          const float* kp = pK + h * D;
+          const float* vp = pV + h * D;
           // K is pre-scaled by log2(e)/sqrt(D): scores live in the log2 domain, weights are 2^(s-m).
           // Only nodes that at least one lane of the warp still needs are visited (warp-uniform loop).
-          auto key = [&](const int j, const bool use) {
-            const float4* kr = reinterpret_cast<const float4*>(kp + j * E);
-            float s = 0.f;
-#pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4) {
-              const float4 kk = kr[d4];
-              s = fmaf(q[d4 * 4], kk.x, s); s = fmaf(q[d4 * 4 + 1], kk.y, s);
-              s = fmaf(q[d4 * 4 + 2], kk.z, s); s = fmaf(q[d4 * 4 + 3], kk.w, s);
-            }
-            if (use) {
-              if (s > m + 12.f) {          // lazy rescale of the running softmax reference
-                const float c = exp2f(m - s);
-                l *= c;
-#pragma unroll
-                for (int d = 0; d < D; ++d) o[d] *= c;
-                m = s;
-              }
-              const float p = exp2f(s - m);
-              l += p;
-              const float4* vr = reinterpret_cast<const float4*>(vp + j * E);
+          for (int w = 0; w < W; ++w) {
+            const uint32_t mw = act ? sMask[r * W + w] : FULL;
+            const int nb = N1 - w * 32;
+            const uint32_t lim = nb >= 32 ? FULL : ((1u << nb) - 1u);
+            uint32_t bits = __reduce_or_sync(FULL, ~mw) & lim;
+            while (bits) {
+              const int jb = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int j = w * 32 + jb;
+              const float4* kr = reinterpret_cast<const float4*>(kp + (size_t)j * E);
+              float s = 0.f;
 #pragma unroll
               for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 vv = vr[d4];
-                o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
-                o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
+                const float4 kk = RESIDENT ? kr[d4] : __ldg(kr + d4);
+                s = fmaf(q[d4 * 4], kk.x, s); s = fmaf(q[d4 * 4 + 1], kk.y, s);
+                s = fmaf(q[d4 * 4 + 2], kk.z, s); s = fmaf(q[d4 * 4 + 3], kk.w, s);
+              }
+              if (!((mw >> jb) & 1u)) {
+                if (s > m + 12.f) {          // lazy rescale of the running softmax reference
+                  const float c = exp2f(m - s);
+                  l *= c;
+#pragma unroll
+                  for (int d = 0; d < D; ++d) o[d] *= c;
+                  m = s;
+                }
+                const float p = exp2f(s - m);
+                l += p;
+                const float4* vr = reinterpret_cast<const float4*>(vp + (size_t)j * E);
+#pragma unroll
+                for (int d4 = 0; d4 < D / 4; ++d4) {
+                  const float4 vv = RESIDENT ? vr[d4] : __ldg(vr + d4);
+                  o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
+                  o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
+                }
               }
             }
-          };
-#define ELG_KEY_WORD(W, MW)                                                              \
-          {                                                                                \
-            const int nb = N1 - (W) * 32;                                                  \
-            const uint32_t lim = nb >= 32 ? FULL : (nb <= 0 ? 0u : ((1u << nb) - 1u));     \
-            uint32_t bits = __reduce_or_sync(FULL, ~(MW)) & lim;                           \
-            while (bits) {                                                                 \
-              const int jb = __ffs(bits) - 1;                                              \
-              bits &= bits - 1;                                                            \
-              key((W) * 32 + jb, !(((MW) >> jb) & 1u));                                    \
-            }                                                                              \
           }
-          ELG_KEY_WORD(0, mw0)
-          ELG_KEY_WORD(1, mw1)
-          ELG_KEY_WORD(2, mw2)
-          ELG_KEY_WORD(3, mw3)
-#undef ELG_KEY_WORD
           if (act) {
             const float inv = 1.f / l;
             float4* op = reinterpret_cast<float4*>(sO + r * E + h * D);
@@ -391,103 +397,101 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             sel[i] = (CVRP && t == 0) ? 0 : A.start_nodes[gr];
           }
         } else {
-          const bool any_live = __any_sync(FULL, row_ok && !sFin[myr]);
-          float acc[4][4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+          const bool rlive = row_ok && !sFin[myr];
+          const bool any_live = __any_sync(FULL, rlive);
+          float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          int bidx[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+          int samp[4] = {-1, -1, -1, -1};
           if (any_live) {
-            // ---- B2: score tile  acc[i][ch] = o[r0+i] . E'[lane + 32 ch] --------------------------
-            int jj[4];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) jj[ch] = min(lane + 32 * ch, N1 - 1);
-            const int nch = (N1 + 31) >> 5;
-            const float* ob = sO + r0 * E;
-            const int rcl[4] = {0, min(1, nrows - 1 - r0), min(2, nrows - 1 - r0), min(3, nrows - 1 - r0)};
-#pragma unroll 4
-            for (int c4 = 0; c4 < E / 4; ++c4) {
-              float4 ov[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) ov[i] = *reinterpret_cast<const float4*>(ob + rcl[i] * E + c4 * 4);
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                if (ch < nch) {
-                  const float4 ev = *reinterpret_cast<const float4*>(sE + jj[ch] * E + ((c4 ^ (jj[ch] & 7)) << 2));
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    acc[i][ch] = fmaf(ov[i].x, ev.x, acc[i][ch]); acc[i][ch] = fmaf(ov[i].y, ev.y, acc[i][ch]);
-                    acc[i][ch] = fmaf(ov[i].z, ev.z, acc[i][ch]); acc[i][ch] = fmaf(ov[i].w, ev.w, acc[i][ch]);
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const float ebv = sEb[jj[ch]];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) acc[i][ch] += ebv;
-            }
-            __syncwarp();
-            // ---- B1: local policy, octet of lanes per row; scratch = this warp's (now dead) o rows ----
-            uint8_t* ids = reinterpret_cast<uint8_t*>(sO + r0 * E);     // [4][64] bytes
-            float* dense = sO + r0 * E + 64;                            // [4][DS]
-            const bool rlive = row_ok && !sFin[myr];
+            // ---- B1: local policy, octet of lanes per row --------------------------------------------
+            uint16_t* ids = reinterpret_cast<uint16_t*>(sm + L.ids) + warp * 4 * KT_MAX + rq * KT_MAX;
             const int cur = sCur[myr];
             const float ldv = sLoad[myr];
-            const float xc = sXY[2 * cur], yc = sXY[2 * cur + 1];
-            // neighbour walk: first k valid entries of the presorted list of `cur`
-            uint4 Lw = make_uint4(0, 0, 0, 0);
-            if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(A.t.nbr + ((size_t)b * N1 + cur) * ELG_NBR_STRIDE) + s8);
-            const int NL = N1 - DEP, iters = (NL + 7) >> 3, kloc = A.k_local;
+            const float xc = pXY[2 * cur], yc = pXY[2 * cur + 1];
+            const int NL = N1 - DEP, kloc = A.k_local;
+            const uint32_t* mrow = sMask + myr * W;
             int cnt = 0;
+            // neighbour walk: first k valid entries of the distance-presorted list of `cur`
+            if (RESIDENT) {
+              uint4 Lw = make_uint4(0, 0, 0, 0);
+              if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_STRIDE) + s8);
+              const int iters = (NL + 7) >> 3;
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-              if (it >= iters) break;
-              const uint32_t wsel = it < 4 ? Lw.x : (it < 8 ? Lw.y : (it < 12 ? Lw.z : Lw.w));
-              const int id = (wsel >> ((it & 3) * 8)) & 0xff;
-              const int e = it * 8 + s8;
-              const bool valid = rlive && e < NL && cnt < kloc && !((sMask[myr * 4 + (id >> 5)] >> (id & 31)) & 1u);
-              const uint32_t bal = __ballot_sync(FULL, valid);
-              const uint32_t mine = (bal >> (lane & 24)) & 0xffu;
-              const int rank = cnt + __popc(mine & ((1u << s8) - 1u));
-              if (valid && rank < kloc) ids[rq * 64 + rank] = (uint8_t)id;
-              cnt += __popc(mine);
-              if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
+              for (int it = 0; it < 16; ++it) {
+                if (it >= iters) break;
+                const uint32_t wsel = it < 4 ? Lw.x : (it < 8 ? Lw.y : (it < 12 ? Lw.z : Lw.w));
+                const int id = (wsel >> ((it & 3) * 8)) & 0xff;
+                const int e = it * 8 + s8;
+                const bool valid = rlive && e < NL && cnt < kloc && !((mrow[id >> 5] >> (id & 31)) & 1u);
+                const uint32_t bal = __ballot_sync(FULL, valid);
+                const uint32_t mine = (bal >> (lane & 24)) & 0xffu;
+                const int rank = cnt + __popc(mine & ((1u << s8) - 1u));
+                if (valid && rank < kloc) ids[rank] = (uint16_t)id;
+                cnt += __popc(mine);
+                if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
+              }
+            } else {
+              const int stride = (NL + 63) & ~63;          // uint16 entries per node, 64-entry blocks
+              const uint16_t* lst = reinterpret_cast<const uint16_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * stride;
+              const int iters = stride >> 6;
+              for (int it = 0; it < iters; ++it) {
+                uint4 Lw = make_uint4(0, 0, 0, 0);
+                if (rlive && cnt < kloc) Lw = __ldg(reinterpret_cast<const uint4*>(lst + it * 64) + s8);
+                const uint32_t wd[4] = {Lw.x, Lw.y, Lw.z, Lw.w};
+                uint32_t vm = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int id = (wd[i >> 1] >> ((i & 1) * 16)) & 0xffff;
+                  const int e = it * 64 + s8 * 8 + i;
+                  const bool valid = rlive && cnt < kloc && e < NL && !((mrow[id >> 5] >> (id & 31)) & 1u);
+                  vm |= (valid ? 1u : 0u) << i;
+                }
+                const int c = __popc(vm);
+                int incl = c;
+                int tt = __shfl_up_sync(FULL, incl, 1); if (s8 >= 1) incl += tt;
+                tt = __shfl_up_sync(FULL, incl, 2); if (s8 >= 2) incl += tt;
+                tt = __shfl_up_sync(FULL, incl, 4); if (s8 >= 4) incl += tt;
+                int rank = cnt + incl - c;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if ((vm >> i) & 1u) {
+                    if (rank < kloc) ids[rank] = (uint16_t)((wd[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+                    ++rank;
+                  }
+                }
+                cnt += __shfl_sync(FULL, incl, (lane & 24) | 7);
+                if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
+              }
             }
             const int kk = min(cnt, kloc);
             const int np = rlive ? kk + DEP : 0;
-            // default penalty xi everywhere (depot / neighbours are overwritten below)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              for (int j = lane; j < N1; j += 32) dense[i * DS + j] = A.xi;
             __syncwarp();
             float dmax = 0.f;
             if (kk > 0) {
-              const int nl = ids[rq * 64 + kk - 1];
-              dmax = dist2(xc - sXY[2 * nl], yc - sXY[2 * nl + 1]);
+              const int nl = ids[kk - 1];
+              dmax = dist2(xc - pXY[2 * nl], yc - pXY[2 * nl + 1]);
             }
-            float f0[MAXE], f1[MAXE], f2[MAXE], pen[MAXE];
+            float f0[MAXE], f1[MAXE], f2[MAXE], addv[MAXE];
             int node[MAXE];
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
               const int p = s8 + 8 * e;
-              f0[e] = f1[e] = f2[e] = pen[e] = 0.f;
+              f0[e] = f1[e] = f2[e] = addv[e] = 0.f;
               node[e] = 0;
               if (p < np && !(DEP && p == 0)) {
-                const int nd = ids[rq * 64 + p - DEP];
+                const int nd = ids[p - DEP];
                 node[e] = nd;
-                const float dx = sXY[2 * nd] - xc, dy = sXY[2 * nd + 1] - yc;
-                const float dd = dist2(xc - sXY[2 * nd], yc - sXY[2 * nd + 1]);
+                const float xn = pXY[2 * nd], yn = pXY[2 * nd + 1];
+                const float dd = dist2(xc - xn, yc - yn);
                 if (CVRP) {
                   f0[e] = dmax != 0.f ? dd / (dmax + 1e-6f) : dd;
-                  pen[e] = dmax != 0.f ? -(dd / dmax) : -dd;
-                  f2[e] = sDem[nd] / ldv;
+                  addv[e] = dmax != 0.f ? -(dd / dmax) : -dd;      // distance penalty
+                  f2[e] = pDem[nd] / ldv;
                 } else {
                   f0[e] = dd / (dmax + 1e-6f);
-                  pen[e] = -f0[e];
+                  addv[e] = -f0[e];
                 }
-                f1[e] = atan2f(dy, dx);
+                f1[e] = atan2f(yn - yc, xn - xc);
               }
             }
             // 4-head attention of the constant query over the local sequence
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
                 float v = -INFINITY;
                 if (p < np) {
                   v = fmaf(u2, f2[e], fmaf(u1, f1[e], u0 * f0[e])) + sT[h * KT_MAX + p];
-                  if (DEP && p == 0 && (sMask[myr * 4] & 1u)) v = -INFINITY;
+                  if (DEP && p == 0 && (mrow[0] & 1u)) v = -INFINITY;
                 }
                 sc[e] = v;
                 mx = fmaxf(mx, v);
@@ -569,84 +573,136 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
               }
             }
 #pragma unroll
-            for (int e = 0; e < MAXE; ++e) {
-              const int p = s8 + 8 * e;
-              if (p < np) {
-                const float locv = (fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e]) / inv_sqrt_le;
-                dense[rq * DS + node[e]] = pen[e] + locv;
+            for (int e = 0; e < MAXE; ++e)     // penalty + local score of this lane's entries
+              addv[e] += (fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e]) / sqrt_le;
+
+            // ---- B2 + B3 over chunks of 128 nodes ------------------------------------------------------
+            const float* ob = sO + r0 * E;
+            float* dense = RESIDENT ? sO + r0 * E : sm + L.dense + warp * 4 * DS;     // [4][DS]
+            const int rcl[4] = {0, min(1, nrows - 1 - r0), min(2, nrows - 1 - r0), min(3, nrows - 1 - r0)};
+            for (int c0n = 0; c0n < N1; c0n += 128) {
+              float acc[4][4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+              int jj[4];
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) jj[ch] = min(c0n + lane + 32 * ch, N1 - 1);
+              const int nch = min(4, (N1 - c0n + 31) >> 5);
+#pragma unroll 4
+              for (int c4 = 0; c4 < E / 4; ++c4) {
+                float4 ov[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ov[i] = *reinterpret_cast<const float4*>(ob + rcl[i] * E + c4 * 4);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                  if (ch < nch) {
+                    const float4* ep = reinterpret_cast<const float4*>(pE + (size_t)jj[ch] * E + ((c4 ^ (jj[ch] & 7)) << 2));
+                    const float4 ev = RESIDENT ? *ep : __ldg(ep);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      acc[i][ch] = fmaf(ov[i].x, ev.x, acc[i][ch]); acc[i][ch] = fmaf(ov[i].y, ev.y, acc[i][ch]);
+                      acc[i][ch] = fmaf(ov[i].z, ev.z, acc[i][ch]); acc[i][ch] = fmaf(ov[i].w, ev.w, acc[i][ch]);
+                    }
+                  }
+                }
               }
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                const float ebv = pEb[jj[ch]];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][ch] += ebv;
+              }
+              __syncwarp();               // resident: every lane is done reading this warp's o rows
+              // penalty + local for this chunk: xi by default, depot / neighbours overwritten by their octet
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) dense[i * DS + lane + 32 * ch] = A.xi;
+              __syncwarp();
+#pragma unroll
+              for (int e = 0; e < MAXE; ++e) {
+                const int p = s8 + 8 * e;
+                const int nd = node[e] - c0n;
+                if (p < np && nd >= 0 && nd < 128) dense[rq * DS + nd] = addv[e];
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = r0 + i;
+                const bool live = r < nrows && !sFin[min(r, nrows - 1)];
+                if (live) {
+                  float lg[4];
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch) {
+                    const int j = c0n + lane + 32 * ch;
+                    float v = -INFINITY;
+                    if (j < N1 && !((sMask[r * W + (j >> 5)] >> lane) & 1u)) v = A.clip * tanhf(acc[i][ch] + dense[i * DS + lane + 32 * ch]);
+                    lg[ch] = v;
+                    if (v > best[i]) { best[i] = v; bidx[i] = j; }
+                  }
+                  if (A.out_logits) {
+                    float* lo = A.out_logits + ((size_t)b * A.M + row0 + r) * N1;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+                      if (c0n + lane + 32 * ch < N1) lo[c0n + lane + 32 * ch] = lg[ch];
+                  }
+                  if (A.mode == ELG_SAMPLE) {       // host guarantees N1 <= 128 (one chunk) in this mode
+                    float bv = best[i];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) bv = fmaxf(bv, __shfl_xor_sync(FULL, bv, off));
+                    float pr[4], tot = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) { pr[ch] = lg[ch] == -INFINITY ? 0.f : expf(lg[ch] - bv); tot += pr[ch]; }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                    const unsigned long long grow = (unsigned long long)b * A.M + row0 + r;
+                    const unsigned long long stp = A.single_step ? A.step_id : (unsigned long long)t;
+                    const uint4 rnd = philox4x32(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)stp, (uint32_t)(stp >> 32)),
+                                                 make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
+                    const float target = ((rnd.x >> 8) + 0.5f) * (1.f / 16777216.f) * tot;
+                    float run = 0.f, pickp = 0.f;
+                    int pick = -1;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                      float inc = pr[ch];
+#pragma unroll
+                      for (int off = 1; off < 32; off <<= 1) {
+                        const float nb = __shfl_up_sync(FULL, inc, off);
+                        if (lane >= off) inc += nb;
+                      }
+                      const float cum = run + inc;
+                      const uint32_t hit = __ballot_sync(FULL, pr[ch] > 0.f && cum >= target);
+                      if (pick < 0 && hit) {
+                        const int src = __ffs(hit) - 1;
+                        pick = src + 32 * ch;
+                        pickp = __shfl_sync(FULL, pr[ch], src);
+                      }
+                      run += __shfl_sync(FULL, inc, 31);
+                    }
+                    if (pick >= 0) { samp[i] = pick; selp[i] = pickp / tot; }
+                  }
+                }
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
-          // ---- B3: logits, argmax / sampling --------------------------------------------------------
+          // ---- first-max argmax across the warp (ties -> lowest index, as torch.argmax); sampling -----
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = r0 + i;
             const bool live = r < nrows && !sFin[min(r, nrows - 1)];
-            float best = -INFINITY;
-            int bidx = 0x7fffffff;
-            float lg[4];
-            if (live) {
-              const float* dn = sO + r0 * E + 64 + i * DS;
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                const int j = lane + 32 * ch;
-                float v = -INFINITY;
-                if (j < N1 && !((sMask[r * 4 + ch] >> lane) & 1u)) v = A.clip * tanhf(acc[i][ch] + dn[j]);
-                lg[ch] = v;
-                if (v > best) { best = v; bidx = j; }
-              }
-              if (A.out_logits) {
-                float* lo = A.out_logits + ((size_t)b * A.M + row0 + r) * N1;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                  if (lane + 32 * ch < N1) lo[lane + 32 * ch] = lg[ch];
-              }
-            }
-            // first-max argmax across the warp (ties -> lowest index, as torch.argmax)
+            float bv = best[i];
+            int bi = bidx[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-              const float ov = __shfl_xor_sync(FULL, best, off);
-              const int oi = __shfl_xor_sync(FULL, bidx, off);
-              if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+              const float ov = __shfl_xor_sync(FULL, bv, off);
+              const int oi = __shfl_xor_sync(FULL, bi, off);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            int choice = live ? bidx : 0;
-            if (A.mode == ELG_SAMPLE && live) {
-              float pr[4], psum = 0.f;
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) { pr[ch] = lg[ch] == -INFINITY ? 0.f : expf(lg[ch] - best); psum += pr[ch]; }
-              float tot = psum;
-#pragma unroll
-              for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
-              const unsigned long long grow = (unsigned long long)b * A.M + row0 + r;
-              const unsigned long long stp = A.single_step ? A.step_id : (unsigned long long)t;
-              const uint4 rnd = philox4x32(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)stp, (uint32_t)(stp >> 32)),
-                                           make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
-              const float target = ((rnd.x >> 8) + 0.5f) * (1.f / 16777216.f) * tot;
-              float run = 0.f;
-              int pick = -1;
-              float pickp = 0.f;
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                float inc = pr[ch];
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                  const float nb = __shfl_up_sync(FULL, inc, off);
-                  if (lane >= off) inc += nb;
-                }
-                const float cum = run + inc;
-                const uint32_t hit = __ballot_sync(FULL, pr[ch] > 0.f && cum >= target);
-                if (pick < 0 && hit) {
-                  const int src = __ffs(hit) - 1;
-                  pick = src + 32 * ch;
-                  pickp = __shfl_sync(FULL, pr[ch], src);
-                }
-                run += __shfl_sync(FULL, inc, 31);
-              }
-              if (pick < 0) { pick = bidx; pickp = 1.f; }     // rounding fell off the end: take the mode
-              choice = pick;
-              selp[i] = pickp / tot;
-            }
+            int choice = live ? bi : 0;
+            if (A.mode == ELG_SAMPLE && live && samp[i] >= 0) choice = samp[i];     // else (rounding fell off the end): the mode
             sel[i] = choice;
           }
         }
@@ -670,32 +726,34 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             const int sl = sel[i];
             const int prev = sCur[r];
             const bool was_fin = sFin[r] != 0;
-            uint32_t vw = lane < 4 ? sVis[r * 4 + lane] : 0u;
-            if (lane == (sl >> 5)) vw |= 1u << (sl & 31);
-            uint32_t mk;
             bool fin = was_fin;
             float ld = 1.f;
             if (CVRP) {
               const bool at_depot = sl == 0;
-              ld = at_depot ? 1.f : sLoad[r] - sDem[sl];
-              if (lane == 0) vw = at_depot ? (vw | 1u) : (vw & ~1u);
-              uint32_t big[4];
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                const int j = lane + 32 * ch;
-                big[ch] = __ballot_sync(FULL, j < N1 && (__fadd_rn(ld, 1e-6f) < sDem[min(j, N1 - 1)]));
+              ld = at_depot ? 1.f : sLoad[r] - pDem[sl];
+              bool allv = true;
+              for (int w = 0; w < W; ++w) {
+                uint32_t vw = sVis[r * W + w];
+                if (w == (sl >> 5)) vw |= 1u << (sl & 31);
+                if (w == 0) vw = at_depot ? (vw | 1u) : (vw & ~1u);
+                const int j = w * 32 + lane;
+                const uint32_t big = __ballot_sync(FULL, j < N1 && (__fadd_rn(ld, 1e-6f) < pDem[min(j, N1 - 1)]));
+                const int nb = N1 - w * 32;
+                const uint32_t fullw = nb >= 32 ? FULL : ((1u << nb) - 1u);
+                allv = allv && ((vw & fullw) == fullw);
+                __syncwarp();
+                if (lane == 0) { sVis[r * W + w] = vw; sMask[r * W + w] = vw | big; }
               }
-              const uint32_t bg = lane == 0 ? big[0] : (lane == 1 ? big[1] : (lane == 2 ? big[2] : big[3]));
-              const int nb = N1 - lane * 32;
-              const uint32_t fullw = nb >= 32 ? FULL : (nb <= 0 ? 0u : ((1u << nb) - 1u));
-              const bool allv = __all_sync(FULL, lane >= 4 || (vw & fullw) == fullw);
               fin = was_fin || allv;
-              mk = vw | bg;
-              if (fin && lane == 0) mk &= ~1u;
+              __syncwarp();
+              if (fin && lane == 0) sMask[r * W] &= ~1u;       // finished rows may stay at the depot
             } else {
-              mk = vw;
+              if (lane == 0) {
+                const uint32_t vw = sVis[r * W + (sl >> 5)] | (1u << (sl & 31));
+                sVis[r * W + (sl >> 5)] = vw;
+                sMask[r * W + (sl >> 5)] = vw;
+              }
             }
-            if (lane < 4) { sVis[r * 4 + lane] = vw; sMask[r * 4 + lane] = mk; }
             warp_live |= !fin;
             if (lane == 0) {
               if (t > 0) {
@@ -704,7 +762,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
                   const float* ux = A.t.unscaled + (size_t)b * N1 * 2;
                   seg = rintf(seglen(ux[2 * prev] - ux[2 * sl], ux[2 * prev + 1] - ux[2 * sl + 1]));
                 } else {
-                  seg = seglen(sXY[2 * prev] - sXY[2 * sl], sXY[2 * prev + 1] - sXY[2 * sl + 1]);
+                  seg = seglen(pXY[2 * prev] - pXY[2 * sl], pXY[2 * prev + 1] - pXY[2 * sl + 1]);
                 }
                 sTlen[r] += seg;
               }
@@ -735,7 +793,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             const float* ux = A.t.unscaled + (size_t)b * N1 * 2;
             len += rintf(seglen(ux[2 * a] - ux[2 * f], ux[2 * a + 1] - ux[2 * f + 1]));
           } else {
-            len += seglen(sXY[2 * a] - sXY[2 * f], sXY[2 * a + 1] - sXY[2 * f + 1]);
+            len += seglen(pXY[2 * a] - pXY[2 * f], pXY[2 * a + 1] - pXY[2 * f + 1]);
           }
         }
         const size_t g = (size_t)b * A.M + row0 + r;
@@ -749,37 +807,80 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-static int pick_tiles(int M) { return (M + MT_MAX - 1) / MT_MAX; }
+struct Plan {
+  bool resident;
+  int maxe, tiles, MT;
+  size_t smem;
+};
+
+static int make_plan(const elg_model_desc* d, int B, int M, int N1, Plan& p) {
+  const int KT = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
+  p.maxe = KT <= 32 ? 4 : (KT <= 48 ? 6 : 8);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  auto tile_rows = [&](int tiles) { return (((M + tiles - 1) / tiles) + 3) & ~3; };
+  p.tiles = (M + MT_MAX - 1) / MT_MAX;
+  // few aug-instances (library instances: B = 8): use as many row tiles as fit one wave of CTAs
+  if (B * p.tiles < sms) {
+    int t2 = sms / B;
+    int max_tiles = (M + 3) / 4;
+    if (t2 > max_tiles) t2 = max_tiles;
+    if (t2 > p.tiles) p.tiles = t2;
+  }
+  p.MT = tile_rows(p.tiles);
+  p.tiles = (M + p.MT - 1) / p.MT;
+  p.resident = N1 <= N_RES_MAX;
+  if (p.resident) {
+    p.smem = (size_t)make_layout(N1, p.MT, p.maxe * 8, true).total * sizeof(float);
+    if (p.smem > 227 * 1024) p.resident = false;
+  }
+  if (!p.resident) {
+    ELG_REQUIRE(N1 <= N_STREAM_MAX, ELG_EUNSUPPORTED, "rollout supports up to %d nodes (got %d)", N_STREAM_MAX, N1);
+    p.smem = (size_t)make_layout(N1, p.MT, p.maxe * 8, false).total * sizeof(float);
+    while (p.smem > 227 * 1024 && p.MT > 4) {      // huge N: shrink the row tile until the bit masks fit
+      p.MT -= 4;
+      p.tiles = (M + p.MT - 1) / p.MT;
+      p.smem = (size_t)make_layout(N1, p.MT, p.maxe * 8, false).total * sizeof(float);
+    }
+    ELG_REQUIRE(p.smem <= 227 * 1024, ELG_EUNSUPPORTED, "row state does not fit in shared memory (N1=%d)", N1);
+  }
+  return ELG_OK;
+}
 
 static int launch_rollout(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) {
-  const int KT = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
-  const int maxe = KT <= 32 ? 4 : (KT <= 48 ? 6 : 8);
-  a.tiles = pick_tiles(a.M);
-  a.MT = (((a.M + a.tiles - 1) / a.tiles) + 3) & ~3;
-  const SmemLayout L = make_layout(a.N1, a.MT, maxe * 8);
-  const size_t smem = (size_t)L.total * sizeof(float);
-  ELG_REQUIRE(a.N1 <= N_RES_MAX, ELG_EUNSUPPORTED,
-              "resident rollout kernel supports up to %d nodes (got %d); the streaming large-N path is not built yet", N_RES_MAX, a.N1);
-  ELG_REQUIRE(smem <= 227 * 1024, ELG_EUNSUPPORTED, "instance does not fit in shared memory (%zu bytes for N1=%d, rows=%d)", smem, a.N1, a.MT);
+  Plan p;
+  int rc = make_plan(d, a.B, a.M, a.N1, p);
+  if (rc) return rc;
+  ELG_REQUIRE(a.mode == ELG_GREEDY || a.N1 <= 128, ELG_EUNSUPPORTED, "sampling is implemented for up to 128 nodes (got %d)", a.N1);
+  a.tiles = p.tiles;
+  a.MT = p.MT;
   int dev = 0, sms = 148;
   ELG_CUDA_OK(cudaGetDevice(&dev));
   ELG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int work = a.B * a.tiles;
   const int grid = work < sms ? work : sms;
-#define ELG_RK(P, ME)                                                                                         \
-  do {                                                                                                        \
-    ELG_CUDA_OK(cudaFuncSetAttribute(rollout_kernel<P, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    rollout_kernel<P, ME><<<grid, RT, smem, st>>>(a);                                                         \
+#define ELG_RK(P, ME, RES)                                                                                   \
+  do {                                                                                                       \
+    ELG_CUDA_OK(cudaFuncSetAttribute(rollout_kernel<P, ME, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)p.smem));                                                          \
+    rollout_kernel<P, ME, RES><<<grid, RT, p.smem, st>>>(a);                                                 \
+  } while (0)
+#define ELG_RK_ME(P, RES)                                                                                    \
+  do {                                                                                                       \
+    if (p.maxe == 4) ELG_RK(P, 4, RES); else if (p.maxe == 6) ELG_RK(P, 6, RES); else ELG_RK(P, 8, RES);      \
   } while (0)
   if (d->problem == ELG_CVRP) {
-    if (maxe == 4) ELG_RK(ELG_CVRP, 4); else if (maxe == 6) ELG_RK(ELG_CVRP, 6); else ELG_RK(ELG_CVRP, 8);
+    if (p.resident) ELG_RK_ME(ELG_CVRP, true); else ELG_RK_ME(ELG_CVRP, false);
   } else {
-    if (maxe == 4) ELG_RK(ELG_TSP, 4); else if (maxe == 6) ELG_RK(ELG_TSP, 6); else ELG_RK(ELG_TSP, 8);
+    if (p.resident) ELG_RK_ME(ELG_TSP, true); else ELG_RK_ME(ELG_TSP, false);
   }
+#undef ELG_RK_ME
 #undef ELG_RK
   ELG_LAUNCH_OK();
   return ELG_OK;
 }
+
+bool rollout_is_resident(int N1) { return N1 <= N_RES_MAX; }
 
 }  // namespace elg
 
@@ -787,10 +888,11 @@ using namespace elg;
 
 extern "C" {
 
-int elg_rollout_tiles(const elg_model_desc* d, int M, int N1) {
-  (void)N1;
-  if (check_desc(d) || M <= 0) return -1;
-  return pick_tiles(M);
+int elg_rollout_tiles(const elg_model_desc* d, int B, int M, int N1) {
+  if (check_desc(d) || M <= 0 || B <= 0) return -1;
+  Plan p;
+  if (make_plan(d, B, M, N1, p)) return -1;
+  return p.tiles;
 }
 
 static int fill_common(const elg_model_desc* d, const float* derived, const elg_tables* t, int B, int M, int N1,

@@ -122,8 +122,8 @@ class CVRPEnv:
         self.load = torch.ones((B, M), device=dev)
         self.finished = torch.zeros((B, M), dtype=torch.bool, device=dev)
         self._finished_u8 = torch.zeros((B, M), dtype=torch.uint8, device=dev)
-        self._visited_bits = torch.zeros((B, M, 4), dtype=torch.int32, device=dev)
-        self._mask_bits = torch.zeros((B, M, 4), dtype=torch.int32, device=dev)
+        self._visited_bits = torch.zeros((B, M, engine.mask_words(N1)), dtype=torch.int32, device=dev)
+        self._mask_bits = torch.zeros((B, M, engine.mask_words(N1)), dtype=torch.int32, device=dev)
         self._counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ninf_mask = None
         self._ninf_shape = (B, M, N1)

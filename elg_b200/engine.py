@@ -114,7 +114,8 @@ class EncodedBatch:
         self.k, self.v, self.e, self.qtab = big[0], big[1], big[2], big[3]
         self.qfirst = big[4] if handle.problem == "tsp" else None
         self.eb = torch.empty((B, N1), dtype=f32, device=dev)
-        self.nbr = torch.empty((B, N1, _lib.NBR_STRIDE), dtype=torch.uint8, device=dev) if N1 <= 128 else None
+        self.nbr = torch.empty(int(lib.elg_nbr_bytes(ELG_CVRP if handle.problem == "cvrp" else ELG_TSP, B, N1)),
+                               dtype=torch.uint8, device=dev)
         self._big = big
         self.tables = _lib.Tables(*[_ptr(x).value for x in (self.xy, self.demand, self.unscaled, self.enc, self.k, self.v,
                                                              self.e, self.eb, self.qtab, self.qfirst, self.nbr)])
@@ -188,7 +189,9 @@ def rollout(batch, M, start_nodes, mode="greedy", seed=0, sync_tours=True):
     dev = batch.xy.device
     B, N1 = batch.B, batch.N1
     t_max = 2 * N1 + 2 if h.problem == "cvrp" else N1
-    tiles = int(lib.elg_rollout_tiles(h.desc, M, N1))
+    tiles = int(lib.elg_rollout_tiles(h.desc, B, M, N1))
+    if tiles <= 0:
+        raise _lib.ElgError("unsupported rollout shape B=%d M=%d N1=%d: %s" % (B, M, N1, lib.elg_last_error().decode()))
     start = torch.as_tensor(start_nodes, dtype=torch.int32).to(dev, non_blocking=True).contiguous()
     if start.numel() != M:
         raise ValueError("start_nodes must have M=%d entries" % M)
@@ -210,15 +213,18 @@ def rollout(batch, M, start_nodes, mode="greedy", seed=0, sync_tours=True):
     return tours, reward, logp, n_steps[:B * tiles]
 
 
+def mask_words(N1):
+    return (int(N1) + 31) // 32
+
+
 def pack_mask_bits(ninf_mask):
-    """(B, M, N1) fp32 {0,-inf} (or bool, True = masked) -> (B, M, 4) int32 bit words."""
+    """(B, M, N1) fp32 {0,-inf} (or bool, True = masked) -> (B, M, ceil(N1/32)) int32 bit words."""
     m = ninf_mask if ninf_mask.dtype == torch.bool else torch.isinf(ninf_mask)
     B, M, N1 = m.shape
-    if N1 > 128:
-        raise _lib.ElgError("bit-mask state supports up to 128 nodes")
-    pad = torch.zeros((B, M, 128), dtype=torch.int64, device=m.device)
+    W = mask_words(N1)
+    pad = torch.zeros((B, M, W * 32), dtype=torch.int64, device=m.device)
     pad[:, :, :N1] = m
-    w = (pad.view(B, M, 4, 32) << torch.arange(32, device=m.device, dtype=torch.int64)).sum(-1)
+    w = (pad.view(B, M, W, 32) << torch.arange(32, device=m.device, dtype=torch.int64)).sum(-1)
     return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
 
 

@@ -78,8 +78,8 @@ class TSPEnv:
         self.current_node = None
         self._actions, self._solutions = [], None
         self.step_state = Step_State(BATCH_IDX=self.BATCH_IDX, POMO_IDX=self.POMO_IDX)
-        self._visited_bits = torch.zeros((B, M, 4), dtype=torch.int32, device=self.device)
-        self._mask_bits = torch.zeros((B, M, 4), dtype=torch.int32, device=self.device)
+        self._visited_bits = torch.zeros((B, M, engine.mask_words(N)), dtype=torch.int32, device=self.device)
+        self._mask_bits = torch.zeros((B, M, engine.mask_words(N)), dtype=torch.int32, device=self.device)
         self._ninf_shape = (B, M, N)
         self._ninf = None
         self.step_state._mask_bits = self._mask_bits

@@ -102,11 +102,16 @@ typedef struct elg_tables {
   float* eb;              /* [B][N1]      score bias    enc . bo / sqrt(E)                       */
   float* qtab;            /* [B][N1][E]   per-node last-node query  Wq_last[:, :E] * enc         */
   float* qfirst;          /* [B][N1][E]   tsp: per-node first-node query; NULL for cvrp          */
-  uint8_t* nbr;           /* [B][N1][ELG_NBR_STRIDE] neighbour lists sorted by distance          */
+  void* nbr;              /* neighbour lists sorted by (distance, index); elg_nbr_bytes() per batch:
+                             N1 <= ELG_MAX_NODES_RESIDENT: uint8 [B][N1][ELG_NBR_STRIDE], 8-way interleaved
+                             larger:                       uint16 [B][N1][ELG_NBR16_STRIDE(NL)], rank order  */
 } elg_tables;
 
-#define ELG_NBR_STRIDE 128     /* bytes per node: up to 128 neighbour ids, 8-way interleaved */
-#define ELG_MAX_NODES_RESIDENT 128
+#define ELG_NBR_STRIDE 128                          /* bytes per node, resident variant               */
+#define ELG_NBR16_STRIDE(NL) (((NL) + 63) & ~63)    /* uint16 entries per node, streaming variant     */
+#define ELG_MAX_NODES_RESIDENT 112                  /* K/V/E' stay in shared memory up to this size   */
+#define ELG_MAX_NODES 8192                          /* largest instance the rollout supports          */
+#define ELG_MASK_WORDS(N1) (((N1) + 31) / 32)       /* uint32 words per row of every bit mask         */
 
 /* ---- introspection ------------------------------------------------------------------- */
 int elg_abi_version(void);
@@ -152,8 +157,10 @@ int elg_encode(const elg_model_desc* desc, const float* weights, const float* de
  *   n_steps [B*tiles]    steps each CTA ran; the batch length T is their maximum
  *   logp [B][M]          sample mode: sum of log-probabilities of the sampled actions (may be NULL)
  *   work_counter         one zero-initialised int32 (dynamic CTA scheduler)
- * elg_rollout_tiles() returns the number of row tiles per aug-instance used for (M, N1). */
-int elg_rollout_tiles(const elg_model_desc* desc, int M, int N1);
+ * elg_rollout_tiles() returns the number of row tiles per aug-instance used for (B, M, N1);
+ * elg_nbr_bytes() the size of elg_tables.nbr.  Sampling mode needs N1 <= 128. */
+int elg_rollout_tiles(const elg_model_desc* desc, int B, int M, int N1);
+size_t elg_nbr_bytes(int problem, int B, int N1);
 int elg_rollout(const elg_model_desc* desc, const float* derived, const elg_tables* t, int B, int M, int N1,
                 const int32_t* start_nodes, int mode, uint64_t seed, int t_max, int16_t* tours, float* reward,
                 int32_t* n_steps, float* logp, int32_t* work_counter, void* stream);
@@ -162,7 +169,7 @@ int elg_rollout(const elg_model_desc* desc, const float* derived, const elg_tabl
  * model.one_step_rollout for the non-forced steps (CVRP/CVRPModel.py:52-73, TSP/TSPModel.py:40-62)
  * = _get_encoding + Decoder.forward + local_policy_att.forward + argmax / multinomial.
  *   cur [B][M] int32; load [B][M] (cvrp); first [B][M] int32 (tsp);
- *   mask_bits [B][M][4] uint32, bit j set = node j masked (-inf in the reference's ninf_mask)
+ *   mask_bits [B][M][ELG_MASK_WORDS(N1)] uint32, bit j set = node j masked (-inf in the reference's ninf_mask)
  *   selected [B][M] int32 out; prob [B][M] out (sample mode, may be NULL);
  *   logits [B][M][N1] out (masked logits = input of the reference's final softmax), may be NULL */
 int elg_decode_step(const elg_model_desc* desc, const float* derived, const elg_tables* t, int B, int M, int N1,
@@ -172,7 +179,7 @@ int elg_decode_step(const elg_model_desc* desc, const float* derived, const elg_
 
 /* ---- environment step ---------------------------------------------------------------------
  * CVRPEnv.step (CVRP/CVRPEnv.py:190-249) / TSPEnv.step (TSP/TSPEnv.py:108-133) on bit-mask state.
- *   visited_bits, mask_bits [B][M][4] uint32 in/out; load [B][M] in/out; finished [B][M] uint8 in/out
+ *   visited_bits, mask_bits [B][M][ELG_MASK_WORDS(N1)] uint32 in/out; load [B][M] in/out; finished [B][M] uint8 in/out
  *   ninf_mask [B][M][N1] optional fp32 {0,-inf} view for API compatibility (may be NULL)
  *   n_unfinished: one int32, incremented per unfinished row (caller zeroes it) */
 int elg_env_step(int problem, const float* demand, int B, int M, int N1, const int32_t* selected, float* load,

@@ -43,6 +43,8 @@ CASES = {
     "cvrp_n100_sharp": dict(problem="cvrp", n=1, N=100, M=100, aug=8, seed=99, wseed=5, gain=6.0, steps=[2, 50], rows_b=[3]),
     "cvrp_n20_noaug": dict(problem="cvrp", n=6, N=20, M=12, aug=1, seed=21, wseed=3, gain=2.0, steps=[2, 9], rows_b=[0, 5]),
     "cvrp_lib": dict(problem="cvrp", n=1, N=37, M=37, aug=8, seed=31, wseed=1234, gain=3.0, steps=[2, 20], rows_b=[0, 7], lib=True),
+    "cvrp_n200": dict(problem="cvrp", n=1, N=200, M=60, aug=8, seed=61, wseed=1234, gain=3.0, steps=[2, 90, 260], rows_b=[0, 5]),
+    "tsp_n150": dict(problem="tsp", n=1, N=150, M=64, aug=8, seed=62, wseed=1234, gain=3.0, steps=[1, 70, 149], rows_b=[0, 5]),
     "tsp_n20": dict(problem="tsp", n=3, N=20, M=20, aug=8, seed=41, wseed=1234, gain=1.0, steps="all", rows_b=[0, 1, 9, 23]),
     "tsp_n20_sharp": dict(problem="tsp", n=2, N=20, M=20, aug=8, seed=42, wseed=77, gain=6.0, steps="all", rows_b=[0, 5, 15]),
     "tsp_n50": dict(problem="tsp", n=2, N=50, M=50, aug=8, seed=43, wseed=1234, gain=3.0, steps=[1, 2, 10, 30, 49], rows_b=[0, 11]),

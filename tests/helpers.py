@@ -9,8 +9,8 @@ from elg_b200.synth import DEFAULT_MODEL_PARAMS, state_dict_checksum, synthetic_
 from oracle import elg_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CVRP_CASES = ["cvrp_n20", "cvrp_n20_sharp", "cvrp_n50", "cvrp_n100", "cvrp_n100_sharp", "cvrp_n20_noaug", "cvrp_lib"]
-TSP_CASES = ["tsp_n20", "tsp_n20_sharp", "tsp_n50", "tsp_n100", "tsp_n30_m10", "tsp_lib"]
+CVRP_CASES = ["cvrp_n20", "cvrp_n20_sharp", "cvrp_n50", "cvrp_n100", "cvrp_n100_sharp", "cvrp_n20_noaug", "cvrp_lib", "cvrp_n200"]
+TSP_CASES = ["tsp_n20", "tsp_n20_sharp", "tsp_n50", "tsp_n100", "tsp_n30_m10", "tsp_lib", "tsp_n150"]
 ALL_CASES = CVRP_CASES + TSP_CASES
 
 

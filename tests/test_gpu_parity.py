@@ -115,8 +115,8 @@ def test_env_step_bit_exact(case):
     B, M, T = tours.shape
     N1 = prob.xy.shape[1]
     load = torch.ones((B, M), device=DEV)
-    vis = torch.zeros((B, M, 4), dtype=torch.int32, device=DEV)
-    msk = torch.zeros((B, M, 4), dtype=torch.int32, device=DEV)
+    vis = torch.zeros((B, M, engine.mask_words(N1)), dtype=torch.int32, device=DEV)
+    msk = torch.zeros((B, M, engine.mask_words(N1)), dtype=torch.int32, device=DEV)
     fin = torch.zeros((B, M), dtype=torch.uint8, device=DEV)
     ninf = torch.zeros((B, M, N1), device=DEV)
     cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
@@ -135,7 +135,7 @@ def test_env_step_bit_exact(case):
             assert (int(cnt.item()) == 0) == (t == T - 1)
 
 
-@pytest.mark.parametrize("name", ["cvrp_n20", "cvrp_lib", "tsp_n20", "tsp_lib", "tsp_n30_m10"])
+@pytest.mark.parametrize("name", ["cvrp_n20", "cvrp_lib", "tsp_n20", "tsp_lib", "tsp_n30_m10", "cvrp_n200", "tsp_n150"])
 def test_stepwise_api_equals_fused(name):
     """Driving the drop-in classes step by step (the reference's protocol) gives the same tours as the
     fused one-launch rollout: both run the same device code."""
@@ -199,7 +199,8 @@ def test_load_problems_bit_exact():
         engine.load_problems("tsp", p.to(DEV), aug=3)
 
 
-@pytest.mark.parametrize("kind,N,M,n", [("cvrp", 100, 100, 6), ("tsp", 100, 100, 6), ("cvrp", 63, 37, 3), ("tsp", 77, 77, 2)])
+@pytest.mark.parametrize("kind,N,M,n", [("cvrp", 100, 100, 6), ("tsp", 100, 100, 6), ("cvrp", 63, 37, 3), ("tsp", 77, 77, 2),
+                                        ("cvrp", 140, 30, 1), ("tsp", 300, 20, 1)])
 def test_fresh_instances_against_oracle(kind, N, M, n):
     """Fresh seeded instances (not fixtures): fused CUDA rollout vs the fp32 oracle rollout on CPU."""
     from elg_b200 import engine
