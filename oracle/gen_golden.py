@@ -43,6 +43,8 @@ CASES = {
     "cvrp_n100_sharp": dict(problem="cvrp", n=1, N=100, M=100, aug=8, seed=99, wseed=5, gain=6.0, steps=[2, 50], rows_b=[3]),
     "cvrp_n20_noaug": dict(problem="cvrp", n=6, N=20, M=12, aug=1, seed=21, wseed=3, gain=2.0, steps=[2, 9], rows_b=[0, 5]),
     "cvrp_lib": dict(problem="cvrp", n=1, N=37, M=37, aug=8, seed=31, wseed=1234, gain=3.0, steps=[2, 20], rows_b=[0, 7], lib=True),
+    "cvrp_x101": dict(problem="cvrp", n=1, N=100, M=100, aug=8, seed=71, wseed=1234, gain=3.0, steps=[2, 60], rows_b=[0, 6], lib=True, vrp_file="X-n101-k25"),
+    "cvrp_x200": dict(problem="cvrp", n=1, N=199, M=199, aug=8, seed=72, wseed=1234, gain=3.0, steps=[2, 150], rows_b=[3], lib=True, vrp_file="X-n200-k36"),
     "cvrp_n200": dict(problem="cvrp", n=1, N=200, M=60, aug=8, seed=61, wseed=1234, gain=3.0, steps=[2, 90, 260], rows_b=[0, 5]),
     "tsp_n150": dict(problem="tsp", n=1, N=150, M=64, aug=8, seed=62, wseed=1234, gain=3.0, steps=[1, 70, 149], rows_b=[0, 5]),
     "tsp_n20": dict(problem="tsp", n=3, N=20, M=20, aug=8, seed=41, wseed=1234, gain=1.0, steps="all", rows_b=[0, 1, 9, 23]),
@@ -86,7 +88,13 @@ def worker(problem, names):
         rec = {}
         if problem == "cvrp":
             batch = synthetic_cvrp_batch(n, N, seed=c["seed"])
-            if c.get("lib"):
+            if c.get("vrp_file"):
+                from elg_b200 import vrplib_io
+                inst = vrplib_io.read_instance(os.path.join(OUT, "vrplib", c["vrp_file"] + ".vrp"))
+                env.load_vrplib_problem(inst, aug_factor=aug)
+                rec["lib_node_coord"], rec["lib_demand"] = inst["node_coord"], inst["demand"]
+                rec["lib_capacity"] = np.array(inst["capacity"])
+            elif c.get("lib"):
                 # library-style instance: integer coordinates / demands, depot = node 0
                 g = torch.Generator().manual_seed(c["seed"])
                 coord = torch.randint(0, 1000, (N + 1, 2), generator=g).numpy().astype(np.float64)

@@ -9,7 +9,7 @@ from elg_b200.synth import DEFAULT_MODEL_PARAMS, state_dict_checksum, synthetic_
 from oracle import elg_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CVRP_CASES = ["cvrp_n20", "cvrp_n20_sharp", "cvrp_n50", "cvrp_n100", "cvrp_n100_sharp", "cvrp_n20_noaug", "cvrp_lib", "cvrp_n200"]
+CVRP_CASES = ["cvrp_n20", "cvrp_n20_sharp", "cvrp_n50", "cvrp_n100", "cvrp_n100_sharp", "cvrp_n20_noaug", "cvrp_lib", "cvrp_n200", "cvrp_x101", "cvrp_x200"]
 TSP_CASES = ["tsp_n20", "tsp_n20_sharp", "tsp_n50", "tsp_n100", "tsp_n30_m10", "tsp_lib", "tsp_n150"]
 ALL_CASES = CVRP_CASES + TSP_CASES
 
@@ -45,7 +45,7 @@ class Golden:
         z = self.z
         if self.kind == "cvrp":
             if self.meta.get("lib"):
-                return O.load_vrplib(z["lib_node_coord"], z["lib_demand"], int(z["lib_capacity"]), self.aug, dtype)
+                return O.load_vrplib(z["lib_node_coord"], z["lib_demand"], float(z["lib_capacity"]), self.aug, dtype)
             return O.load_cvrp(torch.tensor(z["depot"]), torch.tensor(z["loc"]), torch.tensor(z["demand"]), self.aug, dtype)
         if self.meta.get("lib"):
             return O.load_tsplib(z["lib_node_coord"], self.aug, dtype)
@@ -87,3 +87,15 @@ def compare_tours(t_a, t_b):
     pb = torch.zeros(*t_b.shape[:2], T, dtype=torch.int64); pb[:, :, :t_b.shape[2]] = t_b
     same = (pa == pb).all(dim=2)
     return float(same.float().mean()), same
+
+
+def tie_rows(prob, kind, cur, masked, k):
+    """Rows whose k+1 nearest valid nodes contain two exactly equal distances: torch.topk orders such ties
+    in an implementation-defined way (SURVEY 'hard parts'), so rank-dependent logits are not comparable."""
+    N1 = masked.shape[2]
+    row = prob.dist.gather(1, cur[:, :, None].expand(-1, -1, N1))
+    excl = masked.clone()
+    if kind == "cvrp":
+        excl[:, :, 0] = True
+    d = row.masked_fill(excl, float("inf")).sort(dim=-1)[0][:, :, :k + 1]
+    return ((d[:, :, 1:] == d[:, :, :-1]) & ~torch.isinf(d[:, :, 1:])).any(-1)

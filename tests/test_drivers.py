@@ -1,0 +1,87 @@
+"""Library-instance drivers (CVRPLIB / TSPLIB): reader on CPU, end-to-end drivers on the GPU."""
+import os
+import pickle
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, Golden
+from elg_b200 import vrplib_io
+
+VRP = os.path.join(GOLDEN, "vrplib")
+
+
+def test_vrplib_reader_fields():
+    inst = vrplib_io.read_instance(os.path.join(VRP, "X-n101-k25.vrp"))
+    assert inst["dimension"] == 101 and inst["capacity"] == 206
+    assert inst["node_coord"].shape == (101, 2) and inst["demand"].shape == (101,)
+    assert tuple(inst["node_coord"][0]) == (365.0, 689.0) and inst["demand"][0] == 0 and inst["demand"][1] == 38
+    assert list(inst["depot"]) == [0]
+    sol = vrplib_io.read_solution(os.path.join(VRP, "X-n101-k25.sol"))
+    assert sol["cost"] == 27591 and len(sol["routes"]) == 26
+    # the optimal routes are feasible and cost what the file says (rounded EUC_2D)
+    c, d = inst["node_coord"], inst["demand"]
+    total = 0.0
+    seen = set()
+    for r in sol["routes"]:
+        assert sum(d[j] for j in r) <= inst["capacity"]
+        path = [0] + r + [0]
+        total += sum(round(float(np.hypot(*(c[a] - c[b])))) for a, b in zip(path, path[1:]))
+        seen.update(r)
+    assert seen == set(range(1, 101)) and total == sol["cost"]
+
+
+def _config(problem, name="ELG"):
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS
+    return {"name": name, "use_cuda": True, "cuda_device_num": 0, "vrplib_set": "X", "load_checkpoint": None,
+            "params": {"aug_factor": 8}, "model_params": dict(DEFAULT_MODEL_PARAMS[problem])}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["cvrp_x101", "cvrp_x200"])
+def test_vrplib_driver_matches_reference(case, tmp_path):
+    from elg_b200.cvrp import CVRPModel
+    from elg_b200.cvrp.test_vrplib import VRPLib_Tester
+    g = Golden(case)
+    cfg = _config("cvrp")
+    model = CVRPModel(**cfg["model_params"])
+    model.decoder.add_local_policy("cuda:0")
+    model.load_state_dict(g.state_dict())
+    tester = VRPLib_Tester(cfg, model=model)
+    name = g.meta["vrp_file"]
+    res = {}
+    random.seed(g.meta["seed"])
+    sols, rewards = tester.test_on_one_ins(name, res, os.path.join(VRP, name + ".vrp"), os.path.join(VRP, name + ".sol"))
+    ref_best = float((-g.reward()).min())
+    assert res["scale"] == g.meta["N"]
+    assert abs(res["best_cost"] - ref_best) / ref_best < 2e-3
+    same = (sols.cpu()[:, :, :min(sols.shape[2], g.T)] == g.tours()[:, :, :min(sols.shape[2], g.T)]).all(dim=2)
+    assert same.float().mean() > 0.95
+    assert torch.equal(rewards.cpu()[same], g.reward()[same])          # rounded integer costs
+    assert res["gap"] == (res["best_cost"] - 27591.0) / 27591.0 if name == "X-n101-k25" else True
+
+
+@pytest.mark.gpu
+def test_tsplib_driver_matches_reference(tmp_path):
+    from elg_b200.tsp import TSPModel
+    from elg_b200.tsp.test_tsplib import TSPLib_Tester
+    g = Golden("tsp_lib")
+    coords = g.z["lib_node_coord"]
+    d = tmp_path / "TSPLib"
+    d.mkdir()
+    with open(d / "synthetic52.pkl", "wb") as f:
+        pickle.dump([coords, 12345.0], f)
+    cfg = _config("tsp")
+    cfg["tsplib_path"] = str(d)
+    model = TSPModel(**cfg["model_params"])
+    model.decoder.add_local_policy("cuda:0")
+    model.load_state_dict(g.state_dict())
+    tester = TSPLib_Tester(cfg, model=model)
+    random.seed(g.meta["seed"])
+    results = tester.test_on_tsplib(out_dir=str(tmp_path / "out"))
+    rec = results[0]["record"][0]
+    ref_best = float((-g.reward()).min())
+    assert rec["scale"] == 52 and abs(rec["best_cost"] - ref_best) / ref_best < 2e-3
+    assert os.path.exists(tmp_path / "out" / "ELG_tsplib.json")

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ALL_CASES, CVRP_CASES, TSP_CASES, Golden, compare_tours, sub_problem, top2_margin
+from helpers import ALL_CASES, CVRP_CASES, TSP_CASES, Golden, compare_tours, sub_problem, tie_rows, top2_margin
 from oracle import elg_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -57,7 +57,10 @@ def test_teacher_forced_logits_and_choices(case):
                                             want_logits=True)
         logits, sel = logits.cpu(), sel.cpu()
         ref = s["logits"]
-        live = torch.ones(ref.shape[:2], dtype=torch.bool)      # decode_step evaluates every row, finished or not
+        # decode_step evaluates every row, finished or not; rows with exact distance ties among their
+        # nearest neighbours are excluded (torch.topk's tie order is implementation-defined)
+        live = ~tie_rows(sub_problem(prob, rows), g.kind, s["cur"], s["masked"], g.model_params()["local_size"][0])
+        assert live.float().mean() > 0.9
         assert torch.equal(torch.isinf(logits)[live], torch.isinf(ref)[live])
         fin = ~torch.isinf(ref) & live[:, :, None]
         err = (logits[fin] - ref[fin]).abs()
@@ -154,7 +157,7 @@ def test_stepwise_api_equals_fused(name):
     if g.kind == "cvrp":
         if g.meta.get("lib"):
             env.load_vrplib_problem({"node_coord": z["lib_node_coord"], "demand": z["lib_demand"],
-                                     "capacity": int(z["lib_capacity"]), "depot": np.array([0])}, g.aug)
+                                     "capacity": float(z["lib_capacity"]), "depot": np.array([0])}, g.aug)
         else:
             env.load_random_problems({k: torch.tensor(z[k]) for k in ("depot", "loc", "demand")}, g.aug)
     else:
