@@ -114,10 +114,11 @@ def cpu_rollout_rate(n_inst, seed, threads=None):
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path, timed on host cores."""
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     cores = torch.get_num_threads()
     n = args.ref_batch
     times, T = [], 0
@@ -271,6 +272,7 @@ def run_ours(args):
             "mean_aug_cost": mean_cost, "rollout_steps_T": T_list,
         }
         if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
             rate, dt, T = cpu_rollout_rate(args.cpu_sample, INSTANCE_SEED)
             line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d CVRP100 instances (x8 aug x 100 POMO rows), one batch, %.1f s, T=%d; "

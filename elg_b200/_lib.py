@@ -55,12 +55,14 @@ SYMBOLS = {
     "elg_encode": (_I, [C.POINTER(ModelDesc), _P, _P, C.POINTER(Tables), _I, _I, _P, _SZ, _P]),
     "elg_rollout_tiles": (_I, [C.POINTER(ModelDesc), _I, _I, _I]),
     "elg_nbr_bytes": (_SZ, [_I, _I, _I]),
+    "elg_e_bytes": (_SZ, [_I, _I]),
     "elg_rollout": (_I, [C.POINTER(ModelDesc), _P, C.POINTER(Tables), _I, _I, _I, _P, _I, _U64, _I, _P, _P, _P, _P, _P, _P]),
     "elg_decode_step": (_I, [C.POINTER(ModelDesc), _P, C.POINTER(Tables), _I, _I, _I, _P, _P, _P, _P, _I, _U64, _U64,
                              _P, _P, _P, _P]),
     "elg_env_step": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "elg_cur_feature": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "elg_tour_length": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "elg_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 
 

@@ -14,10 +14,12 @@
 //   hid  = relu(x1 W1^T + b1)                 sgemm + bias + relu epilogue
 //   t    = hid W2^T + b2 + x1                 sgemm + bias + residual epilogue
 //   x    = instance_norm(t) * w + b
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace elg {
 
+bool rollout_is_resident(int N1);
 int launch_neighbours(int problem, const float* xy, int B, int N1, void* nbr, cudaStream_t stream);
 
 // ---- embedding --------------------------------------------------------------------------------
@@ -49,7 +51,7 @@ __global__ void embed_kernel(int problem, const float* __restrict__ xy, const fl
 
 // ---- SGEMM  C[M][N] = A[M][K] * B[N][K]^T (+ epilogue) ----------------------------------------
 // 128x128x8 tiles, 256 threads, 8x8 register tile per thread, register-prefetched double buffer.
-enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RES = 3, EPI_SWIZZLE = 4 };
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RES = 3, EPI_SWIZZLE = 4, EPI_UMMA_SPLIT = 5 };
 
 template <int EPI>
 __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
@@ -129,9 +131,31 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
           float4 rr = *reinterpret_cast<const float4*>(res + m * ldc + n);
           v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
         }
-        int nn = n;
-        if (EPI == EPI_SWIZZLE) nn = eswz((int)(m % N1), n);
-        *reinterpret_cast<float4*>(C + m * ldc + nn) = v;
+        if (EPI == EPI_UMMA_SPLIT) {
+          // fp16 hi/lo halves in the K-major core-matrix layout the rollout kernel feeds to tcgen05 (umma.cuh):
+          // per aug-instance [hi | lo], each N1p rows x 128 k; element (j, k) at (k/8)*N1p*16 + (j/8)*128 + (j%8)*16 + (k%8)*2
+          const int N1p = (N1 + 15) & ~15;
+          const long long bi = m / N1;
+          const int j = (int)(m % N1);
+          uint8_t* base = reinterpret_cast<uint8_t*>(C) + bi * ((long long)N1p * 512) + (size_t)(n >> 3) * N1p * 16 +
+                          (j >> 3) * 128 + (j & 7) * 16 + (n & 7) * 2;
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          __half hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            hi[q] = __float2half_rn(vv[q]);
+            lo[q] = __float2half_rn(vv[q] - __half2float(hi[q]));
+          }
+          *reinterpret_cast<uint2*>(base) = make_uint2((uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16),
+                                                       (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16));
+          *reinterpret_cast<uint2*>(base + (size_t)N1p * 256) =
+              make_uint2((uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16),
+                         (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16));
+        } else {
+          int nn = n;
+          if (EPI == EPI_SWIZZLE) nn = eswz((int)(m % N1), n);
+          *reinterpret_cast<float4*>(C + m * ldc + nn) = v;
+        }
       }
     }
 }
@@ -318,7 +342,12 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
   const float* enc = t->enc;
   ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WK4, t->k, nullptr, nullptr, rows, E, E, E, N1, st));
   ELG_TRY(gemm<EPI_NONE>(enc, w + L.dec_wv, t->v, nullptr, nullptr, rows, E, E, E, N1, st));
-  ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, t->e, nullptr, nullptr, rows, E, E, E, N1, st));
+  if (rollout_is_resident(N1)) {
+    ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(B, N1), st));      // padded rows of the MMA operand must be zero
+    ELG_TRY(gemm<EPI_UMMA_SPLIT>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
+  } else {
+    ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
+  }
   ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQN, t->qtab, nullptr, nullptr, rows, E, E, E, N1, st));
   if (d->problem == ELG_TSP)
     ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQF, t->qfirst, nullptr, nullptr, rows, E, E, E, N1, st));

@@ -245,6 +245,12 @@ int elg_load_problems(int problem, const float* depot_xy, const float* node_xy, 
   return ELG_OK;
 }
 
+size_t elg_e_bytes(int B, int N1) {
+  if (B <= 0 || N1 <= 1) return 0;
+  if (N1 <= ELG_MAX_NODES_RESIDENT) return (size_t)B * ((N1 + 15) & ~15) * 512;     // fp16 hi + lo, rows padded to 16
+  return (size_t)B * N1 * 128 * sizeof(float);
+}
+
 size_t elg_nbr_bytes(int problem, int B, int N1) {
   if (B <= 0 || N1 <= 1) return 0;
   if (N1 <= ELG_MAX_NODES_RESIDENT) return (size_t)B * N1 * ELG_NBR_STRIDE;

@@ -27,6 +27,7 @@
 //   phase C  env step on bit masks (fp32 load recurrence, visited / too-large masks by warp ballots).
 #include <string.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace elg {
 
@@ -37,6 +38,8 @@ constexpr int N_RES_MAX = 112;      // nodes the resident variant supports
 constexpr int N_STREAM_MAX = 8192;  // nodes the streaming variant supports (uint16 ids, sort kernel)
 constexpr int DS = 128;             // stride of the per-row dense penalty+local scratch (one node chunk)
 constexpr int TS = 36;              // padded row stride of the VPE / PE tables in smem
+constexpr int SS = 116;             // resident: row stride of the staged scores (112 scores + 4 neighbour-mask words)
+constexpr int A_HALF = 16384;       // resident: bytes of one fp16 A operand (64 rows x 128 k, K-major core matrices)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct RolloutArgs {
@@ -78,8 +81,10 @@ __host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT, bool r
   int o = 0;
   L.k = o; o += resident ? N1 * E : 0;
   L.v = o; o += resident ? N1 * E : 0;
-  L.e = o; o += resident ? N1 * E : 0;
-  L.o = o; o += MT * E;
+  // resident: E' as fp16 hi/lo tcgen05 B operands (N1 padded to 16 rows); attention outputs as fp16 hi/lo
+  // A operands (64 rows; +1 KB because the upper 64 MMA rows alias the next k-chunk); the staged scores alias them
+  L.e = o; o += resident ? 2 * (((N1 + 15) & ~15) * 64) : 0;
+  L.o = o; o += resident ? (2 * A_HALF + 1024) / 4 : MT * E;
   L.eb = o; o += resident ? r4(N1) : 0;
   L.xy = o; o += resident ? r4(2 * N1) : 0;
   L.dem = o; o += resident ? r4(N1) : 0;
@@ -105,7 +110,7 @@ __host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT, bool r
   L.ids = o; o += RW * 4 * (KT_MAX / 2);            // per warp: 4 rows x 64 uint16 neighbour ids
   L.dense = o; o += resident ? 0 : RW * 4 * DS;     // resident: aliases the warp's dead attention rows
   L.ctrl = o; o += 4;
-  L.bar = o; o += 4;
+  L.bar = o; o += 8;                                // TMA mbarrier, MMA mbarrier, TMEM base address
   L.total = o;
   return L;
 }
@@ -188,7 +193,10 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
   uint32_t* sMask = reinterpret_cast<uint32_t*>(sm + L.mask);
   uint32_t* sVis = reinterpret_cast<uint32_t*>(sm + L.vis);
   int* sCtrl = reinterpret_cast<int*>(sm + L.ctrl);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);      // TMA completion
+  uint64_t* bar_mma = bar + 1;                                    // tcgen05.commit completion
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+  const int N1p = (N1 + 15) & ~15;                                // E' rows padded for the MMA N dimension
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -209,13 +217,18 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
     for (int i = tid; i < LE * LE; i += RT) w[L.wct + i] = loc[LOC_WCT + i];
     if (RESIDENT && tid == 0) {
       mbar_init(bar, 1);
+      mbar_init(bar_mma, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (RESIDENT && warp == 0) umma::tmem_alloc(tmem_ptr, 128);     // scores D[128 lanes][<=112 cols] fp32
+    if (RESIDENT) umma::fence_before_sync();
   }
   __syncthreads();
+  uint32_t tmem_d = 0;
+  if (RESIDENT) { umma::fence_after_sync(); tmem_d = *tmem_ptr; }
 
   const int total_work = A.B * A.tiles;
-  uint32_t bar_phase = 0;
+  uint32_t bar_phase = 0, mma_phase = 0;
   const float sqrt_le = 5.656854249492381f;   // sqrt(32), used as a divisor like the reference
 
   for (int iter = 0;; ++iter) {
@@ -240,11 +253,12 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
       float* sEb = sm + L.eb; float* sXY = sm + L.xy; float* sDem = sm + L.dem;
       if (tid == 0) {
         const uint32_t bytes = (uint32_t)N1 * E * sizeof(float);
+        const uint32_t ebytes = (uint32_t)N1p * 512u;        // fp16 hi + lo, N1p rows x 128 k
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, 3 * bytes);
+        mbar_expect_tx(bar, 2 * bytes + ebytes);
         bulk_g2s(sK, A.t.k + (size_t)b * N1 * E, bytes, bar);
         bulk_g2s(sV, A.t.v + (size_t)b * N1 * E, bytes, bar);
-        bulk_g2s(sE, A.t.e + (size_t)b * N1 * E, bytes, bar);
+        bulk_g2s(sE, reinterpret_cast<const uint8_t*>(A.t.e) + (size_t)b * ebytes, ebytes, bar);
       }
       for (int i = tid; i < N1; i += RT) {
         sEb[i] = A.t.eb[(size_t)b * N1 + i];
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
       }
       pK = sK; pV = sV; pE = sE; pEb = sEb; pXY = sXY; pDem = sDem;
     } else {
-      pK = A.t.k + (size_t)b * N1 * E; pV = A.t.v + (size_t)b * N1 * E; pE = A.t.e + (size_t)b * N1 * E;
+      pK = A.t.k + (size_t)b * N1 * E; pV = A.t.v + (size_t)b * N1 * E; pE = reinterpret_cast<const float*>(A.t.e) + (size_t)b * N1 * E;
       pEb = A.t.eb + (size_t)b * N1; pXY = A.t.xy + (size_t)b * N1 * 2;
       pDem = CVRP ? A.t.demand + (size_t)b * N1 : A.t.eb;
     }
@@ -372,22 +386,271 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           }
           if (act) {
             const float inv = 1.f / l;
-            float4* op = reinterpret_cast<float4*>(sO + r * E + h * D);
+            if (RESIDENT) {
+              // fp16 hi/lo A operand of the score MMA: row r, columns h*16 .. h*16+15 = k-chunks 2h, 2h+1
+              uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4)
-              op[d4] = make_float4(o[d4 * 4] * inv, o[d4 * 4 + 1] * inv, o[d4 * 4 + 2] * inv, o[d4 * 4 + 3] * inv);
+              for (int d2 = 0; d2 < D / 2; ++d2) {
+                __half h0, l0, h1, l1;
+                umma::split_f16(o[2 * d2] * inv, h0, l0);
+                umma::split_f16(o[2 * d2 + 1] * inv, h1, l1);
+                hw[d2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lw[d2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              }
+              uint8_t* ah = reinterpret_cast<uint8_t*>(sO) + (2 * h) * 1024 + (r >> 3) * 128 + (r & 7) * 16;
+              *reinterpret_cast<uint4*>(ah) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(ah + 1024) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+              *reinterpret_cast<uint4*>(ah + A_HALF) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              *reinterpret_cast<uint4*>(ah + A_HALF + 1024) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+            } else {
+              float4* op = reinterpret_cast<float4*>(sO + r * E + h * D);
+#pragma unroll
+              for (int d4 = 0; d4 < D / 4; ++d4)
+                op[d4] = make_float4(o[d4 * 4] * inv, o[d4 * 4 + 1] * inv, o[d4 * 4 + 2] * inv, o[d4 * 4 + 3] * inv);
+            }
           }
         }
+        if (RESIDENT) umma::fence_async_smem();     // generic-proxy operand writes -> tensor-core reads
         __syncthreads();
+        if (RESIDENT && tid == 0) {
+          // scores D[row][node] = o . E'  as  A_hi B_hi + A_hi B_lo + A_lo B_hi  (tcgen05, fp32 accumulate in TMEM)
+          umma::fence_after_sync();
+          const uint32_t idesc = umma::make_idesc_f16(128, N1p);
+          const uint32_t a0 = umma::smem_addr(sO), b0 = umma::smem_addr(sm + L.e);
+          const uint32_t lboB = (uint32_t)N1p * 16u, bhalf = (uint32_t)N1p * 256u;
+          bool accum = false;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t aa = a0 + (term == 2 ? A_HALF : 0), bb = b0 + (term == 1 ? bhalf : 0);
+#pragma unroll
+            for (int ks = 0; ks < E / 16; ++ks) {
+              umma::mma_f16_ss(tmem_d, umma::make_desc(aa + ks * 2048, 1024, 128), umma::make_desc(bb + ks * 2 * lboB, lboB, 128),
+                               idesc, accum);
+              accum = true;
+            }
+          }
+          umma::commit(bar_mma);
+        }
       }
 
       // ================= phase B + C: warp = 4 rows ==============================================
       const int r0 = warp * 4;
+      const bool own = r0 < nrows;
+      const int rq = lane >> 3, s8 = lane & 7;         // octet (row within the warp), sub-lane
+      const int myr = own ? min(r0 + rq, nrows - 1) : 0;
+      const bool row_ok = own && (r0 + rq) < nrows;
       int warp_live = 0;
-      if (r0 < nrows) {
-        const int rq = lane >> 3, s8 = lane & 7;       // octet (row within the warp), sub-lane
-        const int myr = min(r0 + rq, nrows - 1);
-        const bool row_ok = (r0 + rq) < nrows;
+      // B1 results: penalty + local score of this lane's neighbour entries (rank p = s8 + 8 e)
+      float addv[MAXE];
+      int node[MAXE];
+      int np = 0;
+      bool rlive = false, any_live = false;
+      if (own && !forced) {
+        rlive = row_ok && !sFin[myr];
+        any_live = __any_sync(FULL, rlive);
+        if (any_live) {
+          // ---- B1: local policy, octet of lanes per row --------------------------------------------
+          uint16_t* ids = reinterpret_cast<uint16_t*>(sm + L.ids) + warp * 4 * KT_MAX + rq * KT_MAX;
+          const int cur = sCur[myr];
+          const float ldv = sLoad[myr];
+          const float xc = pXY[2 * cur], yc = pXY[2 * cur + 1];
+          const int NL = N1 - DEP, kloc = A.k_local;
+          const uint32_t* mrow = sMask + myr * W;
+          int cnt = 0;
+          // neighbour walk: first k valid entries of the distance-presorted list of `cur`
+          if (RESIDENT) {
+            uint4 Lw = make_uint4(0, 0, 0, 0);
+            if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_STRIDE) + s8);
+            const int iters = (NL + 7) >> 3;
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+              if (it >= iters) break;
+              const uint32_t wsel = it < 4 ? Lw.x : (it < 8 ? Lw.y : (it < 12 ? Lw.z : Lw.w));
+              const int id = (wsel >> ((it & 3) * 8)) & 0xff;
+              const int e = it * 8 + s8;
+              const bool valid = rlive && e < NL && cnt < kloc && !((mrow[id >> 5] >> (id & 31)) & 1u);
+              const uint32_t bal = __ballot_sync(FULL, valid);
+              const uint32_t mine = (bal >> (lane & 24)) & 0xffu;
+              const int rank = cnt + __popc(mine & ((1u << s8) - 1u));
+              if (valid && rank < kloc) ids[rank] = (uint16_t)id;
+              cnt += __popc(mine);
+              if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
+            }
+          } else {
+            const int stride = (NL + 63) & ~63;          // uint16 entries per node, 64-entry blocks
+            const uint16_t* lst = reinterpret_cast<const uint16_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * stride;
+            const int iters = stride >> 6;
+            for (int it = 0; it < iters; ++it) {
+              uint4 Lw = make_uint4(0, 0, 0, 0);
+              if (rlive && cnt < kloc) Lw = __ldg(reinterpret_cast<const uint4*>(lst + it * 64) + s8);
+              const uint32_t wd[4] = {Lw.x, Lw.y, Lw.z, Lw.w};
+              uint32_t vm = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int id = (wd[i >> 1] >> ((i & 1) * 16)) & 0xffff;
+                const int e = it * 64 + s8 * 8 + i;
+                const bool valid = rlive && cnt < kloc && e < NL && !((mrow[id >> 5] >> (id & 31)) & 1u);
+                vm |= (valid ? 1u : 0u) << i;
+              }
+              const int c = __popc(vm);
+              int incl = c;
+              int tt = __shfl_up_sync(FULL, incl, 1); if (s8 >= 1) incl += tt;
+              tt = __shfl_up_sync(FULL, incl, 2); if (s8 >= 2) incl += tt;
+              tt = __shfl_up_sync(FULL, incl, 4); if (s8 >= 4) incl += tt;
+              int rank = cnt + incl - c;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if ((vm >> i) & 1u) {
+                  if (rank < kloc) ids[rank] = (uint16_t)((wd[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+                  ++rank;
+                }
+              }
+              cnt += __shfl_sync(FULL, incl, (lane & 24) | 7);
+              if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
+            }
+          }
+          const int kk = min(cnt, kloc);
+          np = rlive ? kk + DEP : 0;
+          __syncwarp();
+          float dmax = 0.f;
+          if (kk > 0) {
+            const int nl = ids[kk - 1];
+            dmax = dist2(xc - pXY[2 * nl], yc - pXY[2 * nl + 1]);
+          }
+          float f0[MAXE], f1[MAXE], f2[MAXE];
+#pragma unroll
+          for (int e = 0; e < MAXE; ++e) {
+            const int p = s8 + 8 * e;
+            f0[e] = f1[e] = f2[e] = addv[e] = 0.f;
+            node[e] = 0;
+            if (p < np && !(DEP && p == 0)) {
+              const int nd = ids[p - DEP];
+              node[e] = nd;
+              const float xn = pXY[2 * nd], yn = pXY[2 * nd + 1];
+              const float dd = dist2(xc - xn, yc - yn);
+              if (CVRP) {
+                f0[e] = dmax != 0.f ? dd / (dmax + 1e-6f) : dd;
+                addv[e] = dmax != 0.f ? -(dd / dmax) : -dd;      // distance penalty
+                f2[e] = pDem[nd] / ldv;
+              } else {
+                f0[e] = dd / (dmax + 1e-6f);
+                addv[e] = -f0[e];
+              }
+              f1[e] = atan2f(yn - yc, xn - xc);
+            }
+          }
+          // 4-head attention of the constant query over the local sequence
+          float mown[4] = {0.f, 0.f, 0.f, 0.f};       // this lane's 4 rows of mh = Wo_l ol + bo_l
+#pragma unroll
+          for (int h = 0; h < LH; ++h) {
+            const float u0 = sU[h * 4], u1 = sU[h * 4 + 1], u2 = sU[h * 4 + 2];
+            float sc[MAXE];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) {
+              const int p = s8 + 8 * e;
+              float v = -INFINITY;
+              if (p < np) {
+                v = fmaf(u2, f2[e], fmaf(u1, f1[e], u0 * f0[e])) + sT[h * KT_MAX + p];
+                if (DEP && p == 0 && (mrow[0] & 1u)) v = -INFINITY;
+              }
+              sc[e] = v;
+              mx = fmaxf(mx, v);
+            }
+            mx = octet_max(mx);
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, sum = 0.f;
+            float vp8[LD];
+#pragma unroll
+            for (int d = 0; d < LD; ++d) vp8[d] = 0.f;
+#pragma unroll
+            for (int e = 0; e < MAXE; ++e) {
+              const int p = s8 + 8 * e;
+              const float w = (p < np && sc[e] != -INFINITY) ? expf(sc[e] - mx) : 0.f;
+              sum += w;
+              g0 = fmaf(w, f0[e], g0); g1 = fmaf(w, f1[e], g1); g2 = fmaf(w, f2[e], g2);
+              if (p < np) {
+                const float4 va = *reinterpret_cast<const float4*>(sVPE + p * TS + h * LD);
+                const float4 vb = *reinterpret_cast<const float4*>(sVPE + p * TS + h * LD + 4);
+                vp8[0] = fmaf(w, va.x, vp8[0]); vp8[1] = fmaf(w, va.y, vp8[1]);
+                vp8[2] = fmaf(w, va.z, vp8[2]); vp8[3] = fmaf(w, va.w, vp8[3]);
+                vp8[4] = fmaf(w, vb.x, vp8[4]); vp8[5] = fmaf(w, vb.y, vp8[5]);
+                vp8[6] = fmaf(w, vb.z, vp8[6]); vp8[7] = fmaf(w, vb.w, vp8[7]);
+              }
+            }
+            sum = octet_sum(sum);
+            const float inv = sum > 0.f ? 1.f / sum : 0.f;
+            g0 = octet_sum(g0) * inv; g1 = octet_sum(g1) * inv; g2 = octet_sum(g2) * inv;
+#pragma unroll
+            for (int d = 0; d < LD; ++d) {
+              const float vps = octet_sum(vp8[d]) * inv;
+              const int c = h * LD + d;
+              // ol[c] = (Wv We)[c] . g + (Wv be)[c] + sum_p w_p (Wv PE(p))[c]
+              const float ol = fmaf(sA[c * 4 + 2], g2, fmaf(sA[c * 4 + 1], g1, sA[c * 4] * g0)) + sCV[c] + vps;
+              const float4 wc = *reinterpret_cast<const float4*>(sWCT + c * LE + s8 * 4);
+              mown[0] = fmaf(wc.x, ol, mown[0]); mown[1] = fmaf(wc.y, ol, mown[1]);
+              mown[2] = fmaf(wc.z, ol, mown[2]); mown[3] = fmaf(wc.w, ol, mown[3]);
+            }
+          }
+          float z0 = 0.f, z1 = 0.f, z2 = 0.f, c0 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = s8 * 4 + i;
+            mown[i] += sBC[c];
+            z0 = fmaf(sWE[c * 4], mown[i], z0); z1 = fmaf(sWE[c * 4 + 1], mown[i], z1);
+            z2 = fmaf(sWE[c * 4 + 2], mown[i], z2); c0 = fmaf(sBE[c], mown[i], c0);
+          }
+          z0 = octet_sum(z0); z1 = octet_sum(z1); z2 = octet_sum(z2); c0 = octet_sum(c0);
+          // loc_p = (We f_p + be + PE(p)) . mh / sqrt(32)
+          float pem[MAXE];
+#pragma unroll
+          for (int e = 0; e < MAXE; ++e) pem[e] = 0.f;
+#pragma unroll
+          for (int src = 0; src < 8; ++src) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float mv = __shfl_sync(FULL, mown[i], (lane & 24) | src);
+              const int c = src * 4 + i;
+#pragma unroll
+              for (int e = 0; e < MAXE; ++e) {
+                const int p = min(s8 + 8 * e, KT - 1);
+                pem[e] = fmaf(sPE[p * TS + c], mv, pem[e]);
+              }
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < MAXE; ++e)     // penalty + local score of this lane's entries
+            addv[e] += (fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e]) / sqrt_le;
+
+        }
+      }
+
+      if (RESIDENT && !forced) {
+        // ---- scores TMEM -> shared memory (+ eb): warps of TMEM lane quadrants 0/1 (rows 0..63), 4 column parts --
+        if ((warp & 3) < 2) {
+          mbar_wait(bar_mma, mma_phase);
+          umma::fence_after_sync();
+          const int q = warp & 3, part = warp >> 2, cp = N1p >> 2;
+          const int row = 32 * q + lane;
+          float* srow = sO + row * SS;
+          for (int c = part * cp; c < (part + 1) * cp; c += 16) {
+            const int cs = max(0, min(c, (part + 1) * cp - 16));
+            float v[16];
+            umma::ld16(tmem_d + ((uint32_t)(32 * q) << 16) + cs, v);
+            if (row < nrows) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int col = cs + i;
+                if (col >= c && col < (part + 1) * cp && col < N1) srow[col] = v[i] + (sm + L.eb)[col];
+              }
+            }
+          }
+          umma::fence_before_sync();
+        }
+        mma_phase ^= 1;
+        __syncthreads();
+      }
+
+      if (own) {
         int sel[4];
         float selp[4] = {1.f, 1.f, 1.f, 1.f};
         if (forced) {
@@ -397,296 +660,209 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             sel[i] = (CVRP && t == 0) ? 0 : A.start_nodes[gr];
           }
         } else {
-          const bool rlive = row_ok && !sFin[myr];
-          const bool any_live = __any_sync(FULL, rlive);
           float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           int bidx[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
           int samp[4] = {-1, -1, -1, -1};
-          if (any_live) {
-            // ---- B1: local policy, octet of lanes per row --------------------------------------------
-            uint16_t* ids = reinterpret_cast<uint16_t*>(sm + L.ids) + warp * 4 * KT_MAX + rq * KT_MAX;
-            const int cur = sCur[myr];
-            const float ldv = sLoad[myr];
-            const float xc = pXY[2 * cur], yc = pXY[2 * cur + 1];
-            const int NL = N1 - DEP, kloc = A.k_local;
-            const uint32_t* mrow = sMask + myr * W;
-            int cnt = 0;
-            // neighbour walk: first k valid entries of the distance-presorted list of `cur`
-            if (RESIDENT) {
-              uint4 Lw = make_uint4(0, 0, 0, 0);
-              if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_STRIDE) + s8);
-              const int iters = (NL + 7) >> 3;
+          if (any_live && RESIDENT) {
+            // ---- B3 (resident): the octet adds penalty + local to its neighbours' staged scores and publishes a
+            //      neighbour bit mask; every other unmasked node gets the default penalty xi
+            {
+              uint32_t nbw[4] = {0u, 0u, 0u, 0u};
+              float* srow = sO + myr * SS;
 #pragma unroll
-              for (int it = 0; it < 16; ++it) {
-                if (it >= iters) break;
-                const uint32_t wsel = it < 4 ? Lw.x : (it < 8 ? Lw.y : (it < 12 ? Lw.z : Lw.w));
-                const int id = (wsel >> ((it & 3) * 8)) & 0xff;
-                const int e = it * 8 + s8;
-                const bool valid = rlive && e < NL && cnt < kloc && !((mrow[id >> 5] >> (id & 31)) & 1u);
-                const uint32_t bal = __ballot_sync(FULL, valid);
-                const uint32_t mine = (bal >> (lane & 24)) & 0xffu;
-                const int rank = cnt + __popc(mine & ((1u << s8) - 1u));
-                if (valid && rank < kloc) ids[rank] = (uint16_t)id;
-                cnt += __popc(mine);
-                if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
-              }
-            } else {
-              const int stride = (NL + 63) & ~63;          // uint16 entries per node, 64-entry blocks
-              const uint16_t* lst = reinterpret_cast<const uint16_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * stride;
-              const int iters = stride >> 6;
-              for (int it = 0; it < iters; ++it) {
-                uint4 Lw = make_uint4(0, 0, 0, 0);
-                if (rlive && cnt < kloc) Lw = __ldg(reinterpret_cast<const uint4*>(lst + it * 64) + s8);
-                const uint32_t wd[4] = {Lw.x, Lw.y, Lw.z, Lw.w};
-                uint32_t vm = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int id = (wd[i >> 1] >> ((i & 1) * 16)) & 0xffff;
-                  const int e = it * 64 + s8 * 8 + i;
-                  const bool valid = rlive && cnt < kloc && e < NL && !((mrow[id >> 5] >> (id & 31)) & 1u);
-                  vm |= (valid ? 1u : 0u) << i;
+              for (int e = 0; e < MAXE; ++e) {
+                const int p = s8 + 8 * e;
+                if (p < np) {
+                  const int nd = node[e];
+                  srow[nd] += addv[e];
+                  const uint32_t bit = 1u << (nd & 31);
+                  nbw[0] |= (nd >> 5) == 0 ? bit : 0u; nbw[1] |= (nd >> 5) == 1 ? bit : 0u;
+                  nbw[2] |= (nd >> 5) == 2 ? bit : 0u; nbw[3] |= (nd >> 5) == 3 ? bit : 0u;
                 }
-                const int c = __popc(vm);
-                int incl = c;
-                int tt = __shfl_up_sync(FULL, incl, 1); if (s8 >= 1) incl += tt;
-                tt = __shfl_up_sync(FULL, incl, 2); if (s8 >= 2) incl += tt;
-                tt = __shfl_up_sync(FULL, incl, 4); if (s8 >= 4) incl += tt;
-                int rank = cnt + incl - c;
+              }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if ((vm >> i) & 1u) {
-                    if (rank < kloc) ids[rank] = (uint16_t)((wd[i >> 1] >> ((i & 1) * 16)) & 0xffff);
-                    ++rank;
+              for (int w = 0; w < 4; ++w) {
+                nbw[w] |= __shfl_xor_sync(FULL, nbw[w], 1);
+                nbw[w] |= __shfl_xor_sync(FULL, nbw[w], 2);
+                nbw[w] |= __shfl_xor_sync(FULL, nbw[w], 4);
+              }
+              if (row_ok && s8 < 4) reinterpret_cast<uint32_t*>(srow)[112 + s8] = s8 == 0 ? nbw[0] : (s8 == 1 ? nbw[1] : (s8 == 2 ? nbw[2] : nbw[3]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r0 + i;
+              const bool live = r < nrows && !sFin[min(r, nrows - 1)];
+              if (live) {
+                const float* srow = sO + r * SS;
+                float lg[4];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                  const int j = lane + 32 * ch;
+                  float v = -INFINITY;
+                  if (j < N1 && !((sMask[r * W + ch] >> lane) & 1u)) {
+                    const bool isnb = (reinterpret_cast<const uint32_t*>(srow)[112 + ch] >> lane) & 1u;
+                    v = A.clip * tanhf(isnb ? srow[j] : srow[j] + A.xi);
+                  }
+                  lg[ch] = v;
+                  if (v > best[i]) { best[i] = v; bidx[i] = j; }
+                }
+                if (A.out_logits) {
+                  float* lo = A.out_logits + ((size_t)b * A.M + row0 + r) * N1;
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch)
+                    if (lane + 32 * ch < N1) lo[lane + 32 * ch] = lg[ch];
+                }
+                if (A.mode == ELG_SAMPLE) {       // host guarantees N1 <= 128 (one chunk) in this mode
+                  float bv = best[i];
+#pragma unroll
+                  for (int off = 16; off > 0; off >>= 1) bv = fmaxf(bv, __shfl_xor_sync(FULL, bv, off));
+                  float pr[4], tot = 0.f;
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch) { pr[ch] = lg[ch] == -INFINITY ? 0.f : expf(lg[ch] - bv); tot += pr[ch]; }
+#pragma unroll
+                  for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                  const unsigned long long grow = (unsigned long long)b * A.M + row0 + r;
+                  const unsigned long long stp = A.single_step ? A.step_id : (unsigned long long)t;
+                  const uint4 rnd = philox4x32(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)stp, (uint32_t)(stp >> 32)),
+                                               make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
+                  const float target = ((rnd.x >> 8) + 0.5f) * (1.f / 16777216.f) * tot;
+                  float run = 0.f, pickp = 0.f;
+                  int pick = -1;
+#pragma unroll
+                  for (int ch = 0; ch < 4; ++ch) {
+                    float inc = pr[ch];
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                      const float nb = __shfl_up_sync(FULL, inc, off);
+                      if (lane >= off) inc += nb;
+                    }
+                    const float cum = run + inc;
+                    const uint32_t hit = __ballot_sync(FULL, pr[ch] > 0.f && cum >= target);
+                    if (pick < 0 && hit) {
+                      const int src = __ffs(hit) - 1;
+                      pick = src + 32 * ch;
+                      pickp = __shfl_sync(FULL, pr[ch], src);
+                    }
+                    run += __shfl_sync(FULL, inc, 31);
+                  }
+                  if (pick >= 0) { samp[i] = pick; selp[i] = pickp / tot; }
+                }
+              }
+            }
+          }
+          if (any_live && !RESIDENT) {
+            // ---- B2 + B3 over chunks of 128 nodes ------------------------------------------------------
+          const float* ob = sO + r0 * E;
+          float* dense = RESIDENT ? sO + r0 * E : sm + L.dense + warp * 4 * DS;     // [4][DS]
+          const int rcl[4] = {0, min(1, nrows - 1 - r0), min(2, nrows - 1 - r0), min(3, nrows - 1 - r0)};
+          for (int c0n = 0; c0n < N1; c0n += 128) {
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+            int jj[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) jj[ch] = min(c0n + lane + 32 * ch, N1 - 1);
+            const int nch = min(4, (N1 - c0n + 31) >> 5);
+#pragma unroll 4
+            for (int c4 = 0; c4 < E / 4; ++c4) {
+              float4 ov[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) ov[i] = *reinterpret_cast<const float4*>(ob + rcl[i] * E + c4 * 4);
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                if (ch < nch) {
+                  const float4* ep = reinterpret_cast<const float4*>(pE + (size_t)jj[ch] * E + ((c4 ^ (jj[ch] & 7)) << 2));
+                  const float4 ev = RESIDENT ? *ep : __ldg(ep);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    acc[i][ch] = fmaf(ov[i].x, ev.x, acc[i][ch]); acc[i][ch] = fmaf(ov[i].y, ev.y, acc[i][ch]);
+                    acc[i][ch] = fmaf(ov[i].z, ev.z, acc[i][ch]); acc[i][ch] = fmaf(ov[i].w, ev.w, acc[i][ch]);
                   }
                 }
-                cnt += __shfl_sync(FULL, incl, (lane & 24) | 7);
-                if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
               }
             }
-            const int kk = min(cnt, kloc);
-            const int np = rlive ? kk + DEP : 0;
-            __syncwarp();
-            float dmax = 0.f;
-            if (kk > 0) {
-              const int nl = ids[kk - 1];
-              dmax = dist2(xc - pXY[2 * nl], yc - pXY[2 * nl + 1]);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const float ebv = pEb[jj[ch]];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i][ch] += ebv;
             }
-            float f0[MAXE], f1[MAXE], f2[MAXE], addv[MAXE];
-            int node[MAXE];
+            __syncwarp();               // resident: every lane is done reading this warp's o rows
+            // penalty + local for this chunk: xi by default, depot / neighbours overwritten by their octet
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) dense[i * DS + lane + 32 * ch] = A.xi;
+            __syncwarp();
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
               const int p = s8 + 8 * e;
-              f0[e] = f1[e] = f2[e] = addv[e] = 0.f;
-              node[e] = 0;
-              if (p < np && !(DEP && p == 0)) {
-                const int nd = ids[p - DEP];
-                node[e] = nd;
-                const float xn = pXY[2 * nd], yn = pXY[2 * nd + 1];
-                const float dd = dist2(xc - xn, yc - yn);
-                if (CVRP) {
-                  f0[e] = dmax != 0.f ? dd / (dmax + 1e-6f) : dd;
-                  addv[e] = dmax != 0.f ? -(dd / dmax) : -dd;      // distance penalty
-                  f2[e] = pDem[nd] / ldv;
-                } else {
-                  f0[e] = dd / (dmax + 1e-6f);
-                  addv[e] = -f0[e];
-                }
-                f1[e] = atan2f(yn - yc, xn - xc);
-              }
+              const int nd = node[e] - c0n;
+              if (p < np && nd >= 0 && nd < 128) dense[rq * DS + nd] = addv[e];
             }
-            // 4-head attention of the constant query over the local sequence
-            float mown[4] = {0.f, 0.f, 0.f, 0.f};       // this lane's 4 rows of mh = Wo_l ol + bo_l
-#pragma unroll
-            for (int h = 0; h < LH; ++h) {
-              const float u0 = sU[h * 4], u1 = sU[h * 4 + 1], u2 = sU[h * 4 + 2];
-              float sc[MAXE];
-              float mx = -INFINITY;
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                float v = -INFINITY;
-                if (p < np) {
-                  v = fmaf(u2, f2[e], fmaf(u1, f1[e], u0 * f0[e])) + sT[h * KT_MAX + p];
-                  if (DEP && p == 0 && (mrow[0] & 1u)) v = -INFINITY;
-                }
-                sc[e] = v;
-                mx = fmaxf(mx, v);
-              }
-              mx = octet_max(mx);
-              float g0 = 0.f, g1 = 0.f, g2 = 0.f, sum = 0.f;
-              float vp8[LD];
-#pragma unroll
-              for (int d = 0; d < LD; ++d) vp8[d] = 0.f;
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                const float w = (p < np && sc[e] != -INFINITY) ? expf(sc[e] - mx) : 0.f;
-                sum += w;
-                g0 = fmaf(w, f0[e], g0); g1 = fmaf(w, f1[e], g1); g2 = fmaf(w, f2[e], g2);
-                if (p < np) {
-                  const float4 va = *reinterpret_cast<const float4*>(sVPE + p * TS + h * LD);
-                  const float4 vb = *reinterpret_cast<const float4*>(sVPE + p * TS + h * LD + 4);
-                  vp8[0] = fmaf(w, va.x, vp8[0]); vp8[1] = fmaf(w, va.y, vp8[1]);
-                  vp8[2] = fmaf(w, va.z, vp8[2]); vp8[3] = fmaf(w, va.w, vp8[3]);
-                  vp8[4] = fmaf(w, vb.x, vp8[4]); vp8[5] = fmaf(w, vb.y, vp8[5]);
-                  vp8[6] = fmaf(w, vb.z, vp8[6]); vp8[7] = fmaf(w, vb.w, vp8[7]);
-                }
-              }
-              sum = octet_sum(sum);
-              const float inv = sum > 0.f ? 1.f / sum : 0.f;
-              g0 = octet_sum(g0) * inv; g1 = octet_sum(g1) * inv; g2 = octet_sum(g2) * inv;
-#pragma unroll
-              for (int d = 0; d < LD; ++d) {
-                const float vps = octet_sum(vp8[d]) * inv;
-                const int c = h * LD + d;
-                // ol[c] = (Wv We)[c] . g + (Wv be)[c] + sum_p w_p (Wv PE(p))[c]
-                const float ol = fmaf(sA[c * 4 + 2], g2, fmaf(sA[c * 4 + 1], g1, sA[c * 4] * g0)) + sCV[c] + vps;
-                const float4 wc = *reinterpret_cast<const float4*>(sWCT + c * LE + s8 * 4);
-                mown[0] = fmaf(wc.x, ol, mown[0]); mown[1] = fmaf(wc.y, ol, mown[1]);
-                mown[2] = fmaf(wc.z, ol, mown[2]); mown[3] = fmaf(wc.w, ol, mown[3]);
-              }
-            }
-            float z0 = 0.f, z1 = 0.f, z2 = 0.f, c0 = 0.f;
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int c = s8 * 4 + i;
-              mown[i] += sBC[c];
-              z0 = fmaf(sWE[c * 4], mown[i], z0); z1 = fmaf(sWE[c * 4 + 1], mown[i], z1);
-              z2 = fmaf(sWE[c * 4 + 2], mown[i], z2); c0 = fmaf(sBE[c], mown[i], c0);
-            }
-            z0 = octet_sum(z0); z1 = octet_sum(z1); z2 = octet_sum(z2); c0 = octet_sum(c0);
-            // loc_p = (We f_p + be + PE(p)) . mh / sqrt(32)
-            float pem[MAXE];
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e) pem[e] = 0.f;
-#pragma unroll
-            for (int src = 0; src < 8; ++src) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float mv = __shfl_sync(FULL, mown[i], (lane & 24) | src);
-                const int c = src * 4 + i;
-#pragma unroll
-                for (int e = 0; e < MAXE; ++e) {
-                  const int p = min(s8 + 8 * e, KT - 1);
-                  pem[e] = fmaf(sPE[p * TS + c], mv, pem[e]);
-                }
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < MAXE; ++e)     // penalty + local score of this lane's entries
-              addv[e] += (fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e]) / sqrt_le;
-
-            // ---- B2 + B3 over chunks of 128 nodes ------------------------------------------------------
-            const float* ob = sO + r0 * E;
-            float* dense = RESIDENT ? sO + r0 * E : sm + L.dense + warp * 4 * DS;     // [4][DS]
-            const int rcl[4] = {0, min(1, nrows - 1 - r0), min(2, nrows - 1 - r0), min(3, nrows - 1 - r0)};
-            for (int c0n = 0; c0n < N1; c0n += 128) {
-              float acc[4][4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-              int jj[4];
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) jj[ch] = min(c0n + lane + 32 * ch, N1 - 1);
-              const int nch = min(4, (N1 - c0n + 31) >> 5);
-#pragma unroll 4
-              for (int c4 = 0; c4 < E / 4; ++c4) {
-                float4 ov[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) ov[i] = *reinterpret_cast<const float4*>(ob + rcl[i] * E + c4 * 4);
+              const int r = r0 + i;
+              const bool live = r < nrows && !sFin[min(r, nrows - 1)];
+              if (live) {
+                float lg[4];
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
-                  if (ch < nch) {
-                    const float4* ep = reinterpret_cast<const float4*>(pE + (size_t)jj[ch] * E + ((c4 ^ (jj[ch] & 7)) << 2));
-                    const float4 ev = RESIDENT ? *ep : __ldg(ep);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      acc[i][ch] = fmaf(ov[i].x, ev.x, acc[i][ch]); acc[i][ch] = fmaf(ov[i].y, ev.y, acc[i][ch]);
-                      acc[i][ch] = fmaf(ov[i].z, ev.z, acc[i][ch]); acc[i][ch] = fmaf(ov[i].w, ev.w, acc[i][ch]);
-                    }
-                  }
+                  const int j = c0n + lane + 32 * ch;
+                  float v = -INFINITY;
+                  if (j < N1 && !((sMask[r * W + (j >> 5)] >> lane) & 1u)) v = A.clip * tanhf(acc[i][ch] + dense[i * DS + lane + 32 * ch]);
+                  lg[ch] = v;
+                  if (v > best[i]) { best[i] = v; bidx[i] = j; }
                 }
-              }
+                if (A.out_logits) {
+                  float* lo = A.out_logits + ((size_t)b * A.M + row0 + r) * N1;
 #pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                const float ebv = pEb[jj[ch]];
+                  for (int ch = 0; ch < 4; ++ch)
+                    if (c0n + lane + 32 * ch < N1) lo[c0n + lane + 32 * ch] = lg[ch];
+                }
+                if (A.mode == ELG_SAMPLE) {       // host guarantees N1 <= 128 (one chunk) in this mode
+                  float bv = best[i];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i][ch] += ebv;
-              }
-              __syncwarp();               // resident: every lane is done reading this warp's o rows
-              // penalty + local for this chunk: xi by default, depot / neighbours overwritten by their octet
+                  for (int off = 16; off > 0; off >>= 1) bv = fmaxf(bv, __shfl_xor_sync(FULL, bv, off));
+                  float pr[4], tot = 0.f;
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+                  for (int ch = 0; ch < 4; ++ch) { pr[ch] = lg[ch] == -INFINITY ? 0.f : expf(lg[ch] - bv); tot += pr[ch]; }
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) dense[i * DS + lane + 32 * ch] = A.xi;
-              __syncwarp();
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                const int nd = node[e] - c0n;
-                if (p < np && nd >= 0 && nd < 128) dense[rq * DS + nd] = addv[e];
-              }
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int r = r0 + i;
-                const bool live = r < nrows && !sFin[min(r, nrows - 1)];
-                if (live) {
-                  float lg[4];
+                  for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                  const unsigned long long grow = (unsigned long long)b * A.M + row0 + r;
+                  const unsigned long long stp = A.single_step ? A.step_id : (unsigned long long)t;
+                  const uint4 rnd = philox4x32(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)stp, (uint32_t)(stp >> 32)),
+                                               make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
+                  const float target = ((rnd.x >> 8) + 0.5f) * (1.f / 16777216.f) * tot;
+                  float run = 0.f, pickp = 0.f;
+                  int pick = -1;
 #pragma unroll
                   for (int ch = 0; ch < 4; ++ch) {
-                    const int j = c0n + lane + 32 * ch;
-                    float v = -INFINITY;
-                    if (j < N1 && !((sMask[r * W + (j >> 5)] >> lane) & 1u)) v = A.clip * tanhf(acc[i][ch] + dense[i * DS + lane + 32 * ch]);
-                    lg[ch] = v;
-                    if (v > best[i]) { best[i] = v; bidx[i] = j; }
-                  }
-                  if (A.out_logits) {
-                    float* lo = A.out_logits + ((size_t)b * A.M + row0 + r) * N1;
+                    float inc = pr[ch];
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch)
-                      if (c0n + lane + 32 * ch < N1) lo[c0n + lane + 32 * ch] = lg[ch];
-                  }
-                  if (A.mode == ELG_SAMPLE) {       // host guarantees N1 <= 128 (one chunk) in this mode
-                    float bv = best[i];
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) bv = fmaxf(bv, __shfl_xor_sync(FULL, bv, off));
-                    float pr[4], tot = 0.f;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) { pr[ch] = lg[ch] == -INFINITY ? 0.f : expf(lg[ch] - bv); tot += pr[ch]; }
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
-                    const unsigned long long grow = (unsigned long long)b * A.M + row0 + r;
-                    const unsigned long long stp = A.single_step ? A.step_id : (unsigned long long)t;
-                    const uint4 rnd = philox4x32(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)stp, (uint32_t)(stp >> 32)),
-                                                 make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
-                    const float target = ((rnd.x >> 8) + 0.5f) * (1.f / 16777216.f) * tot;
-                    float run = 0.f, pickp = 0.f;
-                    int pick = -1;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                      float inc = pr[ch];
-#pragma unroll
-                      for (int off = 1; off < 32; off <<= 1) {
-                        const float nb = __shfl_up_sync(FULL, inc, off);
-                        if (lane >= off) inc += nb;
-                      }
-                      const float cum = run + inc;
-                      const uint32_t hit = __ballot_sync(FULL, pr[ch] > 0.f && cum >= target);
-                      if (pick < 0 && hit) {
-                        const int src = __ffs(hit) - 1;
-                        pick = src + 32 * ch;
-                        pickp = __shfl_sync(FULL, pr[ch], src);
-                      }
-                      run += __shfl_sync(FULL, inc, 31);
+                    for (int off = 1; off < 32; off <<= 1) {
+                      const float nb = __shfl_up_sync(FULL, inc, off);
+                      if (lane >= off) inc += nb;
                     }
-                    if (pick >= 0) { samp[i] = pick; selp[i] = pickp / tot; }
+                    const float cum = run + inc;
+                    const uint32_t hit = __ballot_sync(FULL, pr[ch] > 0.f && cum >= target);
+                    if (pick < 0 && hit) {
+                      const int src = __ffs(hit) - 1;
+                      pick = src + 32 * ch;
+                      pickp = __shfl_sync(FULL, pr[ch], src);
+                    }
+                    run += __shfl_sync(FULL, inc, 31);
                   }
+                  if (pick >= 0) { samp[i] = pick; selp[i] = pickp / tot; }
                 }
               }
-              __syncwarp();
             }
+            __syncwarp();
+          }
           }
           // ---- first-max argmax across the warp (ties -> lowest index, as torch.argmax); sampling -----
 #pragma unroll
@@ -803,6 +979,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
       if (tid == 0) A.n_steps[work] = t;
     }
     __syncthreads();
+  }
+  if (RESIDENT) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_d, 128);
   }
 }
 

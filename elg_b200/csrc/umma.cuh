@@ -1,0 +1,101 @@
+// tcgen05 (5th-gen tensor core) helpers for sm_100a: shared-memory matrix descriptors, instruction
+// descriptors, TMEM allocation / loads, commit -> mbarrier.  Inline PTX only (no CUTLASS dependency).
+//
+// Operand layout used everywhere here: K-major, no swizzle ("interleave"), 16-bit elements.
+//   element (row r, col k) of an operand with R rows lives at
+//       base + (k / 8) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2      [bytes]
+//   i.e. 8x8 "core matrices" of 128 contiguous bytes; SBO = 128 B between 8-row groups, LBO bytes
+//   between consecutive 8-column chunks (normally R * 16).  One MMA consumes K = 16 (two chunks);
+//   the next k-step starts 2 * LBO further.
+//
+// Split precision: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) carries ~22 mantissa bits;
+// D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulated in fp32 in TMEM is fp32-grade for |x| < 6e4.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace elg {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor (SM100 "version 1", SWIZZLE_NONE, K-major)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version 1 (Blackwell)
+  return d;                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE
+}
+
+// 32-bit instruction descriptor for kind::f16, fp16 A/B (K-major), fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {        // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// all previously issued MMAs of this thread complete -> arrive on the mbarrier
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// TMEM -> registers: 16 consecutive fp32 columns of this thread's lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "UWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra UDONE_%=;\n\t"
+      "bra UWAIT_%=;\n\t"
+      "UDONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// fp32 -> (hi, lo) fp16 pair
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+// byte offset of element (r, k) inside a K-major no-swizzle operand with `lbo` bytes between 8-column chunks
+__device__ __forceinline__ uint32_t elem_off(int r, int k, uint32_t lbo) {
+  return (uint32_t)(k >> 3) * lbo + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+
+}  // namespace umma
+}  // namespace elg

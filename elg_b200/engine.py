@@ -109,10 +109,11 @@ class EncodedBatch:
         self.unscaled = None if unscaled is None else unscaled.contiguous().to(f32)
         if self.unscaled is not None and self.unscaled.shape[0] != B:
             self.unscaled = self.unscaled.expand(B, -1, -1).contiguous()
-        big = torch.empty((5 if handle.problem == "tsp" else 4, B, N1, 128), dtype=f32, device=dev)
+        big = torch.empty((4 if handle.problem == "tsp" else 3, B, N1, 128), dtype=f32, device=dev)
         self.enc = torch.empty((B, N1, 128), dtype=f32, device=dev)
-        self.k, self.v, self.e, self.qtab = big[0], big[1], big[2], big[3]
-        self.qfirst = big[4] if handle.problem == "tsp" else None
+        self.k, self.v, self.qtab = big[0], big[1], big[2]
+        self.qfirst = big[3] if handle.problem == "tsp" else None
+        self.e = torch.empty(int(lib.elg_e_bytes(B, N1)), dtype=torch.uint8, device=dev)
         self.eb = torch.empty((B, N1), dtype=f32, device=dev)
         self.nbr = torch.empty(int(lib.elg_nbr_bytes(ELG_CVRP if handle.problem == "cvrp" else ELG_TSP, B, N1)),
                                dtype=torch.uint8, device=dev)

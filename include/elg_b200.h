@@ -98,7 +98,9 @@ typedef struct elg_tables {
   float* enc;             /* [B][N1][E]   encoded nodes                                          */
   float* k;               /* [B][N1][E]   decoder keys, pre-scaled by log2(e)/sqrt(qkv)          */
   float* v;               /* [B][N1][E]   decoder values                                         */
-  float* e;               /* [B][N1][E]   score matrix  E' = enc * Wo^T-fold / sqrt(E), swizzled */
+  void* e;                /* score matrix E' = enc * Wo-fold / sqrt(E); elg_e_bytes() per batch:
+                             N1 <= ELG_MAX_NODES_RESIDENT: fp16 hi/lo tcgen05 operand layout [B][2][E/8][N1p][8]
+                             larger:                       fp32 [B][N1][E], 16-byte chunks XOR-swizzled by (j & 7)  */
   float* eb;              /* [B][N1]      score bias    enc . bo / sqrt(E)                       */
   float* qtab;            /* [B][N1][E]   per-node last-node query  Wq_last[:, :E] * enc         */
   float* qfirst;          /* [B][N1][E]   tsp: per-node first-node query; NULL for cvrp          */
@@ -161,6 +163,7 @@ int elg_encode(const elg_model_desc* desc, const float* weights, const float* de
  * elg_nbr_bytes() the size of elg_tables.nbr.  Sampling mode needs N1 <= 128. */
 int elg_rollout_tiles(const elg_model_desc* desc, int B, int M, int N1);
 size_t elg_nbr_bytes(int problem, int B, int N1);
+size_t elg_e_bytes(int B, int N1);
 int elg_rollout(const elg_model_desc* desc, const float* derived, const elg_tables* t, int B, int M, int N1,
                 const int32_t* start_nodes, int mode, uint64_t seed, int t_max, int16_t* tours, float* reward,
                 int32_t* n_steps, float* logp, int32_t* work_counter, void* stream);
@@ -197,6 +200,13 @@ int elg_cur_feature(const float* xy, const float* demand, const float* load, con
  * aug-instances as in TSPEnv.compute_unscaled_distance); round_edges applies rint() per edge. */
 int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M, int T, int N1, int round_edges,
                     float* out, void* stream);
+
+/* ---- diagnostics -----------------------------------------------------------------------------
+ * One split-precision tcgen05 GEMM  D[128][n] = A[rows_a][k] * B[n][k]^T  (fp16 hi/lo operands, fp32
+ * accumulation in TMEM; terms = 1: hi*hi only, 3: + hi*lo + lo*hi; alias: 64-row A operand whose upper
+ * rows alias the next k-chunk).  Pins the UMMA descriptor / TMEM conventions the kernels rely on. */
+int elg_selftest_umma(const float* a, const float* b, float* d, int rows_a, int n, int k, int alias, int terms,
+                      void* stream);
 
 #ifdef __cplusplus
 }
