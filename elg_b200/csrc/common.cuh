@@ -25,8 +25,8 @@ constexpr int DER_WK4 = DER_WQF + E * E;      // [E][E]  Wk * log2(e) / sqrt(D)
 constexpr int DER_WET = DER_WK4 + E * E;      // [E][E]  WET[i][k] = Wo[k][i] / sqrt(E)
 constexpr int DER_BE = DER_WET + E * E;       // [E]     bo / sqrt(E)
 constexpr int DER_LOC = DER_BE + E;           // local-policy tables
-constexpr int LOC_U = 0;                      // [LH][4]      u_h[f]
-constexpr int LOC_T = LOC_U + LH * 4;         // [LH][KT_MAX] t_h[p]
+constexpr int LOC_U = 0;                      // [LH][4]      u_h[f]      (x log2 e)
+constexpr int LOC_T = LOC_U + LH * 4;         // [LH][KT_MAX] t_h[p]      (x log2 e)
 constexpr int LOC_A = LOC_T + LH * KT_MAX;    // [LE][4]      (Wv We)[c][f]
 constexpr int LOC_CV = LOC_A + LE * 4;        // [LE]         Wv be
 constexpr int LOC_VPE = LOC_CV + LE;          // [KT_MAX][LE] Wv PE(p)

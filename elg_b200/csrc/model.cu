@@ -76,7 +76,7 @@ __global__ void prepare_kernel(elg_model_desc d, elg_weight_layout_t L, const fl
     loc[LOC_PE + i] = v;
   }
   __syncthreads();
-  const double inv_sqrt_d = 1.0 / sqrt((double)LD);
+  const double inv_sqrt_d = 1.4426950408889634 / sqrt((double)LD);   // log2(e)/sqrt(d): local softmax runs in the log2 domain
   // u_h[f] and t_h[p]
   for (int i = tid; i < LH * 4; i += nt) {
     int h = i / 4, f = i % 4;

@@ -353,33 +353,46 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             const uint32_t lim = nb >= 32 ? FULL : ((1u << nb) - 1u);
             uint32_t bits = __reduce_or_sync(FULL, ~mw) & lim;
             while (bits) {
-              const int jb = __ffs(bits) - 1;
+              // two nodes per iteration: both score dot products are in flight before the softmax update
+              const int jb0 = __ffs(bits) - 1;
               bits &= bits - 1;
-              const int j = w * 32 + jb;
-              const float4* kr = reinterpret_cast<const float4*>(kp + (size_t)j * E);
-              float s = 0.f;
+              const bool two = bits != 0;
+              const int jb1 = two ? __ffs(bits) - 1 : jb0;
+              bits &= bits - 1;
+              const float4* kr0 = reinterpret_cast<const float4*>(kp + (size_t)(w * 32 + jb0) * E);
+              const float4* kr1 = reinterpret_cast<const float4*>(kp + (size_t)(w * 32 + jb1) * E);
+              float s0 = 0.f, s1 = 0.f;
 #pragma unroll
               for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 kk = RESIDENT ? kr[d4] : __ldg(kr + d4);
-                s = fmaf(q[d4 * 4], kk.x, s); s = fmaf(q[d4 * 4 + 1], kk.y, s);
-                s = fmaf(q[d4 * 4 + 2], kk.z, s); s = fmaf(q[d4 * 4 + 3], kk.w, s);
+                const float4 ka = RESIDENT ? kr0[d4] : __ldg(kr0 + d4);
+                const float4 kb = RESIDENT ? kr1[d4] : __ldg(kr1 + d4);
+                s0 = fmaf(q[d4 * 4], ka.x, s0); s0 = fmaf(q[d4 * 4 + 1], ka.y, s0);
+                s0 = fmaf(q[d4 * 4 + 2], ka.z, s0); s0 = fmaf(q[d4 * 4 + 3], ka.w, s0);
+                s1 = fmaf(q[d4 * 4], kb.x, s1); s1 = fmaf(q[d4 * 4 + 1], kb.y, s1);
+                s1 = fmaf(q[d4 * 4 + 2], kb.z, s1); s1 = fmaf(q[d4 * 4 + 3], kb.w, s1);
               }
-              if (!((mw >> jb) & 1u)) {
-                if (s > m + 12.f) {          // lazy rescale of the running softmax reference
-                  const float c = exp2f(m - s);
-                  l *= c;
+              const bool u0 = !((mw >> jb0) & 1u), u1 = two && !((mw >> jb1) & 1u);
+              const float smax = fmaxf(u0 ? s0 : -INFINITY, u1 ? s1 : -INFINITY);
+              if (smax > m + 12.f) {          // lazy rescale of the running softmax reference
+                const float c = exp2f(m - smax);
+                l *= c;
 #pragma unroll
-                  for (int d = 0; d < D; ++d) o[d] *= c;
-                  m = s;
-                }
-                const float p = exp2f(s - m);
-                l += p;
-                const float4* vr = reinterpret_cast<const float4*>(vp + (size_t)j * E);
+                for (int d = 0; d < D; ++d) o[d] *= c;
+                m = smax;
+              }
+              const float p0 = u0 ? exp2f(s0 - m) : 0.f, p1 = u1 ? exp2f(s1 - m) : 0.f;
+              l += p0 + p1;
+              if (u0 || u1) {
+                const float4* vr0 = reinterpret_cast<const float4*>(vp + (size_t)(w * 32 + jb0) * E);
+                const float4* vr1 = reinterpret_cast<const float4*>(vp + (size_t)(w * 32 + jb1) * E);
 #pragma unroll
                 for (int d4 = 0; d4 < D / 4; ++d4) {
-                  const float4 vv = RESIDENT ? vr[d4] : __ldg(vr + d4);
-                  o[d4 * 4] = fmaf(p, vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p, vv.y, o[d4 * 4 + 1]);
-                  o[d4 * 4 + 2] = fmaf(p, vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p, vv.w, o[d4 * 4 + 3]);
+                  const float4 va = RESIDENT ? vr0[d4] : __ldg(vr0 + d4);
+                  const float4 vb = RESIDENT ? vr1[d4] : __ldg(vr1 + d4);
+                  o[d4 * 4] = fmaf(p0, va.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p0, va.y, o[d4 * 4 + 1]);
+                  o[d4 * 4 + 2] = fmaf(p0, va.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p0, va.w, o[d4 * 4 + 3]);
+                  o[d4 * 4] = fmaf(p1, vb.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p1, vb.y, o[d4 * 4 + 1]);
+                  o[d4 * 4 + 2] = fmaf(p1, vb.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p1, vb.w, o[d4 * 4 + 3]);
                 }
               }
             }
@@ -565,7 +578,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
               const int p = s8 + 8 * e;
-              const float w = (p < np && sc[e] != -INFINITY) ? expf(sc[e] - mx) : 0.f;
+              const float w = (p < np && sc[e] != -INFINITY) ? exp2f(sc[e] - mx) : 0.f;
               sum += w;
               g0 = fmaf(w, f0[e], g0); g1 = fmaf(w, f1[e], g1); g2 = fmaf(w, f2[e], g2);
               if (p < np) {
