@@ -353,26 +353,32 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             const uint32_t lim = nb >= 32 ? FULL : ((1u << nb) - 1u);
             uint32_t bits = __reduce_or_sync(FULL, ~mw) & lim;
             while (bits) {
-              // two nodes per iteration: both score dot products are in flight before the softmax update
-              const int jb0 = __ffs(bits) - 1;
-              bits &= bits - 1;
-              const bool two = bits != 0;
-              const int jb1 = two ? __ffs(bits) - 1 : jb0;
-              bits &= bits - 1;
-              const float4* kr0 = reinterpret_cast<const float4*>(kp + (size_t)(w * 32 + jb0) * E);
-              const float4* kr1 = reinterpret_cast<const float4*>(kp + (size_t)(w * 32 + jb1) * E);
-              float s0 = 0.f, s1 = 0.f;
+              // NK nodes per iteration: all score dot products are in flight before the softmax update
+              constexpr int NK = 4;
+              int jb[NK];
+              bool uu[NK];
+              float sc[NK];
+#pragma unroll
+              for (int n = 0; n < NK; ++n) {
+                const bool have = bits != 0;
+                jb[n] = have ? __ffs(bits) - 1 : jb[0];
+                uu[n] = have && !((mw >> jb[n]) & 1u);
+                bits &= bits - 1;
+                sc[n] = 0.f;
+              }
 #pragma unroll
               for (int d4 = 0; d4 < D / 4; ++d4) {
-                const float4 ka = RESIDENT ? kr0[d4] : __ldg(kr0 + d4);
-                const float4 kb = RESIDENT ? kr1[d4] : __ldg(kr1 + d4);
-                s0 = fmaf(q[d4 * 4], ka.x, s0); s0 = fmaf(q[d4 * 4 + 1], ka.y, s0);
-                s0 = fmaf(q[d4 * 4 + 2], ka.z, s0); s0 = fmaf(q[d4 * 4 + 3], ka.w, s0);
-                s1 = fmaf(q[d4 * 4], kb.x, s1); s1 = fmaf(q[d4 * 4 + 1], kb.y, s1);
-                s1 = fmaf(q[d4 * 4 + 2], kb.z, s1); s1 = fmaf(q[d4 * 4 + 3], kb.w, s1);
+#pragma unroll
+                for (int n = 0; n < NK; ++n) {
+                  const float4* kr = reinterpret_cast<const float4*>(kp + (size_t)(w * 32 + jb[n]) * E) + d4;
+                  const float4 kk = RESIDENT ? *kr : __ldg(kr);
+                  sc[n] = fmaf(q[d4 * 4], kk.x, sc[n]); sc[n] = fmaf(q[d4 * 4 + 1], kk.y, sc[n]);
+                  sc[n] = fmaf(q[d4 * 4 + 2], kk.z, sc[n]); sc[n] = fmaf(q[d4 * 4 + 3], kk.w, sc[n]);
+                }
               }
-              const bool u0 = !((mw >> jb0) & 1u), u1 = two && !((mw >> jb1) & 1u);
-              const float smax = fmaxf(u0 ? s0 : -INFINITY, u1 ? s1 : -INFINITY);
+              float smax = -INFINITY;
+#pragma unroll
+              for (int n = 0; n < NK; ++n) smax = fmaxf(smax, uu[n] ? sc[n] : -INFINITY);
               if (smax > m + 12.f) {          // lazy rescale of the running softmax reference
                 const float c = exp2f(m - smax);
                 l *= c;
@@ -380,19 +386,19 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
                 for (int d = 0; d < D; ++d) o[d] *= c;
                 m = smax;
               }
-              const float p0 = u0 ? exp2f(s0 - m) : 0.f, p1 = u1 ? exp2f(s1 - m) : 0.f;
-              l += p0 + p1;
-              if (u0 || u1) {
-                const float4* vr0 = reinterpret_cast<const float4*>(vp + (size_t)(w * 32 + jb0) * E);
-                const float4* vr1 = reinterpret_cast<const float4*>(vp + (size_t)(w * 32 + jb1) * E);
+              float pp[NK];
+#pragma unroll
+              for (int n = 0; n < NK; ++n) { pp[n] = uu[n] ? exp2f(sc[n] - m) : 0.f; l += pp[n]; }
+              if (smax != -INFINITY) {
 #pragma unroll
                 for (int d4 = 0; d4 < D / 4; ++d4) {
-                  const float4 va = RESIDENT ? vr0[d4] : __ldg(vr0 + d4);
-                  const float4 vb = RESIDENT ? vr1[d4] : __ldg(vr1 + d4);
-                  o[d4 * 4] = fmaf(p0, va.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p0, va.y, o[d4 * 4 + 1]);
-                  o[d4 * 4 + 2] = fmaf(p0, va.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p0, va.w, o[d4 * 4 + 3]);
-                  o[d4 * 4] = fmaf(p1, vb.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(p1, vb.y, o[d4 * 4 + 1]);
-                  o[d4 * 4 + 2] = fmaf(p1, vb.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(p1, vb.w, o[d4 * 4 + 3]);
+#pragma unroll
+                  for (int n = 0; n < NK; ++n) {
+                    const float4* vr = reinterpret_cast<const float4*>(vp + (size_t)(w * 32 + jb[n]) * E) + d4;
+                    const float4 vv = RESIDENT ? *vr : __ldg(vr);
+                    o[d4 * 4] = fmaf(pp[n], vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(pp[n], vv.y, o[d4 * 4 + 1]);
+                    o[d4 * 4 + 2] = fmaf(pp[n], vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(pp[n], vv.w, o[d4 * 4 + 3]);
+                  }
                 }
               }
             }
