@@ -36,7 +36,15 @@ constexpr int LOC_BC = LOC_WCT + LE * LE;     // [LE]
 constexpr int LOC_WE = LOC_BC + LE;           // [LE][4]      We[c][f]
 constexpr int LOC_BE = LOC_WE + LE * 4;       // [LE]
 constexpr int LOC_TOTAL = LOC_BE + LE;
-constexpr int DER_TOTAL = DER_LOC + LOC_TOTAL;
+constexpr int DER_FOLD_TOTAL = DER_LOC + LOC_TOTAL;
+// After the folds: every GEMM weight matrix pre-split into fp16 hi/lo tcgen05 B-operand tiles (one float's worth
+// of bytes per weight element).  Matrix W[N][K] -> tiles (n/128, k/64), each [hi 16 KB | lo 16 KB] in the K-major
+// core-matrix layout of umma.cuh.  Order: per layer {Wq|Wk|Wv (3E x E), Wo, W1, W2}; then K' weights, Wv_dec,
+// Wq_node, Wq_first.
+__host__ __device__ inline long long split_layer_floats(int ff) { return 3LL * E * E + (long long)E * E + 2LL * ff * E; }
+__host__ __device__ inline long long split_off_layer(int l, int ff) { return DER_FOLD_TOTAL + l * split_layer_floats(ff); }
+__host__ __device__ inline long long split_off_dec(int layers, int ff) { return DER_FOLD_TOTAL + layers * split_layer_floats(ff); }
+__host__ __device__ inline long long derived_total(int layers, int ff) { return split_off_dec(layers, ff) + 4LL * E * E; }
 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);

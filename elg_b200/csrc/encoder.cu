@@ -16,6 +16,7 @@
 //   x    = instance_norm(t) * w + b
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace elg {
 
@@ -158,6 +159,144 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
         }
       }
     }
+}
+
+
+// ---- tcgen05 GEMM  C[M][N] = A[M][K] * W[N][K]^T (+ bias / relu / residual) ---------------------------------
+// Split precision: x = hi + lo (fp16 pair, ~22 mantissa bits); D = A_hi W_hi + A_hi W_lo + A_lo W_hi accumulated in
+// fp32 in TMEM (two accumulators: hi*hi | cross terms; fp32-matmul-grade accuracy, tools/umma_precision_experiment.py)
+// -- plain TF32/BF16 inputs would break the 1e-4 logit tolerance.  One CTA = 128 rows; the fp32 activations are split on the fly into the K-major
+// core-matrix operand layout (umma.cuh), the weights were pre-split at model load (split_weights_kernel) and arrive
+// by TMA bulk copy, 32 KB per (n-tile, 64-wide k-block).  96 KB smem -> 2 CTAs/SM hide each other's TMA / MMA latency.
+constexpr int TG_SMEM = 65536 + 32768 + 64;
+
+__device__ __forceinline__ void tg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tg_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   umma::smem_addr(dst)), "l"(src), "r"(bytes), "r"(umma::smem_addr(bar)) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 2) tc_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Ws,
+                                                         float* __restrict__ C, const float* __restrict__ bias,
+                                                         const float* __restrict__ res, long long M, int N, int K, int ldc) {
+  extern __shared__ __align__(1024) uint8_t tsm[];
+  uint8_t* aHi = tsm;                  // 128 rows x 128 k (one k super-block), fp16 hi
+  uint8_t* aLo = tsm + 32768;
+  uint8_t* bT = tsm + 65536;           // [hi 16 KB | lo 16 KB] weight tile: 128 rows (n) x 64 k
+  uint64_t* barB = reinterpret_cast<uint64_t*>(tsm + 98304);
+  uint64_t* barM = barB + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(barB + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * 128;
+  if (warp == 0) umma::tmem_alloc(tptr, 256);      // accumulator 0: hi*hi, accumulator 1 (cols 128..): cross terms
+  if (tid == 0) { umma::mbar_init(barB, 1); umma::mbar_init(barM, 1); }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = *tptr;
+  const int nT = N >> 7, kS = K >> 7;
+  const uint32_t idesc = umma::make_idesc_f16(128, 128);
+  uint32_t phB = 0, phM = 0;
+  for (int nt = 0; nt < nT; ++nt) {
+    for (int ks = 0; ks < kS; ++ks) {
+      if (nt == 0 || kS > 1) {           // (re)build the A operand of this 128-wide k super-block
+        for (int i = tid; i < 128 * 32; i += 256) {
+          const int r = i >> 5, k4 = (i & 31) * 4;
+          const long long row = m0 + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < M) v = *reinterpret_cast<const float4*>(A + row * K + ks * 128 + k4);
+          __half h0, l0, h1, l1, h2, l2, h3, l3;
+          umma::split_f16(v.x, h0, l0); umma::split_f16(v.y, h1, l1);
+          umma::split_f16(v.z, h2, l2); umma::split_f16(v.w, h3, l3);
+          const uint32_t off = umma::elem_off(r, k4, 2048);
+          *reinterpret_cast<uint2*>(aHi + off) = make_uint2((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16),
+                                                            (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16));
+          *reinterpret_cast<uint2*>(aLo + off) = make_uint2((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16),
+                                                            (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16));
+        }
+        umma::fence_async_smem();
+      }
+      for (int half = 0; half < 2; ++half) {
+        __syncthreads();                 // A operand written; every thread is past the previous MMA wait (B tile free)
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tg_mbar_expect_tx(barB, 32768);
+          tg_bulk_g2s(bT, Ws + ((size_t)nt * (K >> 6) + ks * 2 + half) * 32768, 32768, barB);
+          umma::mbar_wait(barB, phB);
+          umma::fence_after_sync();
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a = umma::smem_addr(term == 2 ? aLo : aHi) + half * 8 * 2048;
+            const uint32_t b = umma::smem_addr(bT) + (term == 1 ? 16384 : 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              // the small cross terms get their own accumulator: added into the large hi*hi sums, the tensor core's
+              // internal alignment would truncate them (measured 4x error, tools/umma_precision_experiment.py)
+              umma::mma_f16_ss(tbase + (term ? 128u : 0u), umma::make_desc(a + kk * 4096, 2048, 128),
+                               umma::make_desc(b + kk * 4096, 2048, 128), idesc,
+                               !(ks == 0 && half == 0 && (term == 0 || term == 1) && kk == 0));
+          }
+          umma::commit(barM);
+        }
+        phB ^= 1;
+        umma::mbar_wait(barM, phM);
+        phM ^= 1;
+        umma::fence_after_sync();
+      }
+    }
+    // epilogue: TMEM lane = row; warp quadrant = 32 rows, warp / 4 = 64-column half
+    {
+      const int q = warp & 3, ch = warp >> 2;
+      const long long row = m0 + 32 * q + lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = ch * 64 + c * 16;
+        float v[16], v2[16];
+        umma::ld16(tbase + ((uint32_t)(32 * q) << 16) + col0, v);
+        umma::ld16(tbase + ((uint32_t)(32 * q) << 16) + 128 + col0, v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+        if (row < M) {
+          const int n = nt * 128 + col0;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            float4 o = make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + n + i4 * 4);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (EPI == EPI_BIAS_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (EPI == EPI_BIAS_RES) {
+              const float4 rr = *reinterpret_cast<const float4*>(res + row * ldc + n + i4 * 4);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(C + row * ldc + n + i4 * 4) = o;
+          }
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();                     // accumulator reads done before the next n-tile overwrites TMEM
+  }
+  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+}
+
+template <int EPI>
+static int tc_gemm(const float* A, const float* derived, long long split_off, float* C, const float* bias, const float* res,
+                   long long M, int N, int K, int ldc, cudaStream_t st) {
+  ELG_REQUIRE(N % 128 == 0 && K % 128 == 0, ELG_EUNSUPPORTED, "tc_gemm needs N%%128==0 and K%%128==0 (N=%d K=%d)", N, K);
+  static bool attr = false;
+  if (!attr) {
+    ELG_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+    attr = true;
+  }
+  tc_gemm_kernel<EPI><<<(unsigned)((M + 127) / 128), 256, TG_SMEM, st>>>(A, reinterpret_cast<const uint8_t*>(derived + split_off), C,
+                                                                        bias, res, M, N, K, ldc);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
 }
 
 // ---- encoder self-attention: one CTA per (aug-instance, head) --------------------------------------
@@ -327,30 +466,32 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
   for (int l = 0; l < d->layers; ++l) {
     const auto& y = L.layer[l];
     float* xout = (l == d->layers - 1) ? t->enc : x;
-    ELG_TRY(gemm<EPI_NONE>(x, w + y.wq, qkv, nullptr, nullptr, rows, 3 * E, E, 3 * E, N1, st));
+    const long long so = split_off_layer(l, d->ff);
+    ELG_TRY(tc_gemm<EPI_NONE>(x, derived, so, qkv, nullptr, nullptr, rows, 3 * E, E, 3 * E, st));
     enc_attention_kernel<<<(unsigned)(B * H), 128, att_smem, st>>>(qkv, N1, att);
     ELG_LAUNCH_OK();
-    ELG_TRY(gemm<EPI_BIAS_RES>(att, w + y.wo, tt, w + y.bo, x, rows, E, E, E, N1, st));
+    ELG_TRY(tc_gemm<EPI_BIAS_RES>(att, derived, so + 3LL * E * E, tt, w + y.bo, x, rows, E, E, E, st));
     instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n1w, w + y.n1b, N1, x1);
     ELG_LAUNCH_OK();
-    ELG_TRY(gemm<EPI_BIAS_RELU>(x1, w + y.w1, hid, w + y.b1, nullptr, rows, d->ff, E, d->ff, N1, st));
-    ELG_TRY(gemm<EPI_BIAS_RES>(hid, w + y.w2, tt, w + y.b2, x1, rows, E, d->ff, E, N1, st));
+    ELG_TRY(tc_gemm<EPI_BIAS_RELU>(x1, derived, so + 4LL * E * E, hid, w + y.b1, nullptr, rows, d->ff, E, d->ff, st));
+    ELG_TRY(tc_gemm<EPI_BIAS_RES>(hid, derived, so + 4LL * E * E + (long long)d->ff * E, tt, w + y.b2, x1, rows, E, d->ff, E, st));
     instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n2w, w + y.n2b, N1, xout);
     ELG_LAUNCH_OK();
   }
   // decoder-side tables from the encoded nodes
   const float* enc = t->enc;
-  ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WK4, t->k, nullptr, nullptr, rows, E, E, E, N1, st));
-  ELG_TRY(gemm<EPI_NONE>(enc, w + L.dec_wv, t->v, nullptr, nullptr, rows, E, E, E, N1, st));
+  const long long sd = split_off_dec(d->layers, d->ff);
+  ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd, t->k, nullptr, nullptr, rows, E, E, E, st));
+  ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 1LL * E * E, t->v, nullptr, nullptr, rows, E, E, E, st));
   if (rollout_is_resident(N1)) {
     ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(B, N1), st));      // padded rows of the MMA operand must be zero
     ELG_TRY(gemm<EPI_UMMA_SPLIT>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
   } else {
     ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
   }
-  ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQN, t->qtab, nullptr, nullptr, rows, E, E, E, N1, st));
+  ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 2LL * E * E, t->qtab, nullptr, nullptr, rows, E, E, E, st));
   if (d->problem == ELG_TSP)
-    ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WQF, t->qfirst, nullptr, nullptr, rows, E, E, E, N1, st));
+    ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 3LL * E * E, t->qfirst, nullptr, nullptr, rows, E, E, E, st));
   row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
   ELG_LAUNCH_OK();
   if (t->nbr) ELG_TRY(launch_neighbours(d->problem, t->xy, B, N1, t->nbr, st));

@@ -2,7 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <cuda_fp16.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace elg {
 
@@ -25,7 +27,7 @@ int check_desc(const elg_model_desc* d) {
   ELG_REQUIRE(d->local_emb == LE && d->local_heads == LH && d->local_qkv == LD, ELG_EUNSUPPORTED,
               "kernels are built for local_att 32/4/8 (got %d/%d/%d)", d->local_emb, d->local_heads, d->local_qkv);
   ELG_REQUIRE(d->layers >= 1 && d->layers <= ELG_MAX_LAYERS, ELG_EUNSUPPORTED, "encoder_layer_num %d not in [1,%d]", d->layers, ELG_MAX_LAYERS);
-  ELG_REQUIRE(d->ff > 0 && d->ff % 64 == 0, ELG_EUNSUPPORTED, "ff_hidden_dim must be a positive multiple of 64");
+  ELG_REQUIRE(d->ff > 0 && d->ff % 128 == 0, ELG_EUNSUPPORTED, "ff_hidden_dim must be a positive multiple of 128");
   int kt = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
   ELG_REQUIRE(d->local_k >= 1 && kt <= KT_MAX, ELG_EUNSUPPORTED, "local_size %d outside [1,%d]", d->local_k, KT_MAX - 1);
   ELG_REQUIRE((d->flags & ELG_FLAG_ENSEMBLE) && (d->flags & ELG_FLAG_DISTANCE_PENALTY), ELG_EUNSUPPORTED,
@@ -125,6 +127,20 @@ __global__ void prepare_kernel(elg_model_desc d, elg_weight_layout_t L, const fl
   }
 }
 
+// W[N][K] (fp32, leading dimension ld) -> fp16 hi/lo B-operand tiles for tc_gemm_kernel
+__global__ void split_weights_kernel(const float* __restrict__ w, int N, int K, int ld, uint8_t* __restrict__ out) {
+  const long long total = (long long)N * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    __half hi, lo;
+    umma::split_f16(w[(long long)n * ld + k], hi, lo);
+    uint8_t* tile = out + ((long long)(n >> 7) * (K >> 6) + (k >> 6)) * 32768;
+    const uint32_t off = umma::elem_off(n & 127, k & 63, 2048);
+    *reinterpret_cast<__half*>(tile + off) = hi;
+    *reinterpret_cast<__half*>(tile + 16384 + off) = lo;
+  }
+}
+
 }  // namespace elg
 
 using namespace elg;
@@ -173,15 +189,37 @@ int elg_weight_layout(const elg_model_desc* d, elg_weight_layout_t* L) {
   return ELG_OK;
 }
 
-int64_t elg_derived_floats(const elg_model_desc* d) { return check_desc(d) ? -1 : (int64_t)DER_TOTAL; }
+int64_t elg_derived_floats(const elg_model_desc* d) { return check_desc(d) ? -1 : (int64_t)derived_total(d->layers, d->ff); }
 
 int elg_prepare_model(const elg_model_desc* d, const float* weights, float* derived, void* stream) {
   elg_weight_layout_t L;
   int rc = elg_weight_layout(d, &L);
   if (rc) return rc;
   ELG_REQUIRE(weights && derived, ELG_EINVAL, "NULL weights/derived");
-  prepare_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*d, L, weights, derived);
+  cudaStream_t st = (cudaStream_t)stream;
+  prepare_kernel<<<1, 256, 0, st>>>(*d, L, weights, derived);
   ELG_LAUNCH_OK();
+  // pre-split every GEMM weight into tcgen05 operand tiles (read back by TMA in tc_gemm_kernel)
+  auto split = [&](const float* w, int N, int K, long long off_floats) -> int {
+    split_weights_kernel<<<148, 256, 0, st>>>(w, N, K, K, reinterpret_cast<uint8_t*>(derived + off_floats));
+    ELG_LAUNCH_OK();
+    return ELG_OK;
+  };
+  for (int l = 0; l < d->layers; ++l) {
+    long long o = split_off_layer(l, d->ff);
+    if ((rc = split(weights + L.layer[l].wq, 3 * E, E, o))) return rc;          // Wq|Wk|Wv are contiguous
+    o += 3LL * E * E;
+    if ((rc = split(weights + L.layer[l].wo, E, E, o))) return rc;
+    o += (long long)E * E;
+    if ((rc = split(weights + L.layer[l].w1, d->ff, E, o))) return rc;
+    o += (long long)d->ff * E;
+    if ((rc = split(weights + L.layer[l].w2, E, d->ff, o))) return rc;
+  }
+  long long o = split_off_dec(d->layers, d->ff);
+  if ((rc = split(derived + DER_WK4, E, E, o))) return rc;
+  if ((rc = split(weights + L.dec_wv, E, E, o + 1LL * E * E))) return rc;
+  if ((rc = split(derived + DER_WQN, E, E, o + 2LL * E * E))) return rc;
+  if ((rc = split(derived + DER_WQF, E, E, o + 3LL * E * E))) return rc;
   return ELG_OK;
 }
 

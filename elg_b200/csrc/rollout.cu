@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
       mbar_init(bar_mma, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (RESIDENT && warp == 0) umma::tmem_alloc(tmem_ptr, 128);     // scores D[128 lanes][<=112 cols] fp32
+    if (RESIDENT && warp == 0) umma::tmem_alloc(tmem_ptr, 256);     // scores: hi*hi in cols [0,112), cross terms in [128,240)
     if (RESIDENT) umma::fence_before_sync();
   }
   __syncthreads();
@@ -443,8 +443,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             const uint32_t aa = a0 + (term == 2 ? A_HALF : 0), bb = b0 + (term == 1 ? bhalf : 0);
 #pragma unroll
             for (int ks = 0; ks < E / 16; ++ks) {
-              umma::mma_f16_ss(tmem_d, umma::make_desc(aa + ks * 2048, 1024, 128), umma::make_desc(bb + ks * 2 * lboB, lboB, 128),
-                               idesc, accum);
+              // cross terms accumulate separately: added into the large hi*hi sums they would be truncated
+              umma::mma_f16_ss(tmem_d + (term ? 128u : 0u), umma::make_desc(aa + ks * 2048, 1024, 128),
+                               umma::make_desc(bb + ks * 2 * lboB, lboB, 128), idesc, accum && !(term == 1 && ks == 0));
               accum = true;
             }
           }
@@ -653,8 +654,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           float* srow = sO + row * SS;
           for (int c = part * cp; c < (part + 1) * cp; c += 16) {
             const int cs = max(0, min(c, (part + 1) * cp - 16));
-            float v[16];
+            float v[16], v2[16];
             umma::ld16(tmem_d + ((uint32_t)(32 * q) << 16) + cs, v);
+            umma::ld16(tmem_d + ((uint32_t)(32 * q) << 16) + 128 + cs, v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v2[i];
             if (row < nrows) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -1002,7 +1006,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
   if (RESIDENT) {
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem_d, 128);
+    if (warp == 0) umma::tmem_dealloc(tmem_d, 256);
   }
 }
 

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
     *reinterpret_cast<__half*>(bLo + umma::elem_off(r, k, lboB)) = lo;
   }
   umma::fence_async_smem();
-  if (warp == 0) umma::tmem_alloc(tptr, 128);
+  if (warp == 0) umma::tmem_alloc(tptr, 256);
   if (tid == 0) umma::mbar_init(bar, 1);
   umma::fence_before_sync();
   __syncthreads();
@@ -47,14 +47,18 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
 
   if (tid == 0) {
     const uint32_t idesc = umma::make_idesc_f16(128, N);
+    // terms == 5: hi*hi into accumulator 0, the two cross terms into accumulator 1 (columns 128..), summed on read-out
+    const bool split_acc = terms == 5;
+    const int nterms = split_acc ? 3 : terms;
     bool acc = false;
-    for (int term = 0; term < terms; ++term) {
-      const uint8_t* a = term == 2 ? aLo : aHi;
-      const uint8_t* b = term == 1 ? bLo : bHi;
+    for (int term = 0; term < nterms; ++term) {
+      if (split_acc && term == 1) acc = false;
+      const uint8_t* a = term >= 2 ? aLo : aHi;
+      const uint8_t* b = (term == 1 || term == 3) ? bLo : bHi;
       for (int ks = 0; ks < K / 16; ++ks) {
         const uint64_t ad = umma::make_desc(umma::smem_addr(a) + ks * 2 * lboA, lboA, 128);
         const uint64_t bd = umma::make_desc(umma::smem_addr(b) + ks * 2 * lboB, lboB, 128);
-        umma::mma_f16_ss(tbase, ad, bd, idesc, acc);
+        umma::mma_f16_ss(tbase + ((split_acc && term >= 1) ? 128u : 0u), ad, bd, idesc, acc);
         acc = true;
       }
     }
@@ -65,11 +69,16 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   for (int c = 0; c < N; c += 16) {
     float v[16];
     umma::ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
+    if (terms == 5) {
+      float v2[16];
+      umma::ld16(tbase + ((uint32_t)(warp * 32) << 16) + 128 + c, v2);
+      for (int i = 0; i < 16; ++i) v[i] += v2[i];
+    }
     for (int i = 0; i < 16; ++i) D[(size_t)(warp * 32 + lane) * N + c + i] = v[i];
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tbase, 128);
+  if (warp == 0) umma::tmem_dealloc(tbase, 256);
 }
 
 }  // namespace elg
@@ -80,7 +89,7 @@ extern "C" int elg_selftest_umma(const float* a, const float* b, float* d, int r
                                  void* stream) {
   ELG_REQUIRE(a && b && d, ELG_EINVAL, "NULL pointer");
   ELG_REQUIRE(n % 16 == 0 && n >= 16 && n <= 128 && k % 16 == 0 && k >= 16 && k <= 128, ELG_EINVAL, "need N,K multiples of 16 in [16,128]");
-  ELG_REQUIRE(rows_a >= 1 && rows_a <= (alias ? 64 : 128) && terms >= 1 && terms <= 3, ELG_EINVAL, "bad rows/terms");
+  ELG_REQUIRE(rows_a >= 1 && rows_a <= (alias ? 64 : 128) && terms >= 1 && terms <= 5, ELG_EINVAL, "bad rows/terms");
   const int chunks = k / 8;
   const size_t sizeA = (size_t)chunks * (alias ? 64 : 128) * 16 + (alias ? 1024 : 0), sizeB = (size_t)chunks * n * 16;
   const size_t smem = 2 * sizeA + 2 * sizeB + 64;

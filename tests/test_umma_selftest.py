@@ -25,6 +25,10 @@ def test_split_precision_gemm(rows, n, k, alias):
     got, ref = _run(rows, n, k, alias, 3)
     err = (got - ref).abs().max() / ref.abs().max()
     assert err < 3e-6, err
+    got5, _ = _run(rows, n, k, alias, 5)          # cross terms in their own accumulator: fp32-matmul-grade
+    err5 = (got5 - ref).abs().mean() / ref.abs().mean()
+    fp32 = ((ref.float().double() - ref).abs().mean() / ref.abs().mean())
+    assert err5 < 6e-7 and err5 < 0.6 * ((got - ref).abs().mean() / ref.abs().mean()) + 1e-7, (err5, fp32)
     got1, _ = _run(rows, n, k, alias, 1)          # hi*hi only: fp16-grade, proves the lo terms matter
     err1 = (got1 - ref).abs().max() / ref.abs().max()
     assert 1e-5 < err1 < 5e-3, err1
