@@ -54,8 +54,9 @@ SYMBOLS = {
     "elg_encode_workspace_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
     "elg_encode": (_I, [C.POINTER(ModelDesc), _P, _P, C.POINTER(Tables), _I, _I, _P, _SZ, _P]),
     "elg_rollout_tiles": (_I, [C.POINTER(ModelDesc), _I, _I, _I]),
-    "elg_nbr_bytes": (_SZ, [_I, _I, _I]),
-    "elg_e_bytes": (_SZ, [_I, _I]),
+    "elg_rollout_resident": (_I, [C.POINTER(ModelDesc), _I]),
+    "elg_nbr_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
+    "elg_e_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
     "elg_rollout": (_I, [C.POINTER(ModelDesc), _P, C.POINTER(Tables), _I, _I, _I, _P, _I, _U64, _I, _P, _P, _P, _P, _P, _P]),
     "elg_decode_step": (_I, [C.POINTER(ModelDesc), _P, C.POINTER(Tables), _I, _I, _I, _P, _P, _P, _P, _I, _U64, _U64,
                              _P, _P, _P, _P]),

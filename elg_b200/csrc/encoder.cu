@@ -20,8 +20,8 @@
 
 namespace elg {
 
-bool rollout_is_resident(int N1);
-int launch_neighbours(int problem, const float* xy, int B, int N1, void* nbr, cudaStream_t stream);
+bool rollout_is_resident(const elg_model_desc* d, int N1);
+int launch_neighbours(const elg_model_desc* d, const float* xy, int B, int N1, void* nbr, cudaStream_t stream);
 
 // ---- embedding --------------------------------------------------------------------------------
 __global__ void embed_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand,
@@ -483,8 +483,8 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
   const long long sd = split_off_dec(d->layers, d->ff);
   ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd, t->k, nullptr, nullptr, rows, E, E, E, st));
   ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 1LL * E * E, t->v, nullptr, nullptr, rows, E, E, E, st));
-  if (rollout_is_resident(N1)) {
-    ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(B, N1), st));      // padded rows of the MMA operand must be zero
+  if (rollout_is_resident(d, N1)) {
+    ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(d, B, N1), st));      // padded rows of the MMA operand must be zero
     ELG_TRY(gemm<EPI_UMMA_SPLIT>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
   } else {
     ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
@@ -494,7 +494,7 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
     ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 3LL * E * E, t->qfirst, nullptr, nullptr, rows, E, E, E, st));
   row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
   ELG_LAUNCH_OK();
-  if (t->nbr) ELG_TRY(launch_neighbours(d->problem, t->xy, B, N1, t->nbr, st));
+  if (t->nbr) ELG_TRY(launch_neighbours(d, t->xy, B, N1, t->nbr, st));
   return ELG_OK;
 }
 

@@ -4,6 +4,8 @@
 
 namespace elg {
 
+bool rollout_is_resident(const elg_model_desc* d, int N1);
+
 // ---- x8 augmentation + depot/node concatenation ---------------------------------------------
 // reference: augment_xy_data_by_8_fold (CVRP/utils.py:69-87), load_random_problems (CVRP/CVRPEnv.py:125-150)
 __global__ void load_problems_kernel(int problem, const float* __restrict__ depot, const float* __restrict__ nodes,
@@ -245,16 +247,21 @@ int elg_load_problems(int problem, const float* depot_xy, const float* node_xy, 
   return ELG_OK;
 }
 
-size_t elg_e_bytes(int B, int N1) {
-  if (B <= 0 || N1 <= 1) return 0;
-  if (N1 <= ELG_MAX_NODES_RESIDENT) return (size_t)B * ((N1 + 15) & ~15) * 512;     // fp16 hi + lo, rows padded to 16
+int elg_rollout_resident(const elg_model_desc* d, int N1) {
+  if (check_desc(d) || N1 <= 1) return -1;
+  return rollout_is_resident(d, N1) ? 1 : 0;
+}
+
+size_t elg_e_bytes(const elg_model_desc* d, int B, int N1) {
+  if (check_desc(d) || B <= 0 || N1 <= 1) return 0;
+  if (rollout_is_resident(d, N1)) return (size_t)B * ((N1 + 15) & ~15) * 512;     // fp16 hi + lo, rows padded to 16
   return (size_t)B * N1 * 128 * sizeof(float);
 }
 
-size_t elg_nbr_bytes(int problem, int B, int N1) {
-  if (B <= 0 || N1 <= 1) return 0;
-  if (N1 <= ELG_MAX_NODES_RESIDENT) return (size_t)B * N1 * ELG_NBR_STRIDE;
-  const int NL = N1 - (problem == ELG_CVRP ? 1 : 0);
+size_t elg_nbr_bytes(const elg_model_desc* d, int B, int N1) {
+  if (check_desc(d) || B <= 0 || N1 <= 1) return 0;
+  if (rollout_is_resident(d, N1)) return (size_t)B * N1 * ELG_NBR_STRIDE;
+  const int NL = N1 - (d->problem == ELG_CVRP ? 1 : 0);
   return (size_t)B * N1 * ELG_NBR16_STRIDE(NL) * sizeof(uint16_t);
 }
 
@@ -306,9 +313,9 @@ int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M
 // resident variant (N1 <= 112): uint8 ids, 8-way interleaved, ELG_NBR_STRIDE bytes per node;
 // streaming variant: uint16 ids in rank order, ELG_NBR16_STRIDE(NL) entries per node.
 namespace elg {
-bool rollout_is_resident(int N1);
-int launch_neighbours(int problem, const float* xy, int B, int N1, void* nbr, cudaStream_t stream) {
-  if (rollout_is_resident(N1)) {
+int launch_neighbours(const elg_model_desc* d, const float* xy, int B, int N1, void* nbr, cudaStream_t stream) {
+  const int problem = d->problem;
+  if (rollout_is_resident(d, N1)) {
     neighbour_kernel<<<(unsigned)B * N1, 128, 0, stream>>>(problem, xy, N1, reinterpret_cast<uint8_t*>(nbr));
     ELG_LAUNCH_OK();
     return ELG_OK;

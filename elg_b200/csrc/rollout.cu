@@ -1011,6 +1011,15 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// Resident (K'/V/E' in shared memory for the whole rollout) iff the layout fits with the largest row tile.
+// A function of (model, N1) only, because elg_encode must write E' and the neighbour lists in the matching format.
+bool rollout_is_resident(const elg_model_desc* d, int N1) {
+  if (N1 > N_RES_MAX) return false;
+  const int KT = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
+  const int maxe = KT <= 32 ? 4 : (KT <= 48 ? 6 : 8);
+  return (size_t)make_layout(N1, MT_MAX, maxe * 8, true).total * sizeof(float) <= 227 * 1024;
+}
+
 struct Plan {
   bool resident;
   int maxe, tiles, MT;
@@ -1033,11 +1042,8 @@ static int make_plan(const elg_model_desc* d, int B, int M, int N1, Plan& p) {
   }
   p.MT = tile_rows(p.tiles);
   p.tiles = (M + p.MT - 1) / p.MT;
-  p.resident = N1 <= N_RES_MAX;
-  if (p.resident) {
-    p.smem = (size_t)make_layout(N1, p.MT, p.maxe * 8, true).total * sizeof(float);
-    if (p.smem > 227 * 1024) p.resident = false;
-  }
+  p.resident = rollout_is_resident(d, N1);      // the same predicate elg_encode used to choose the table formats
+  if (p.resident) p.smem = (size_t)make_layout(N1, p.MT, p.maxe * 8, true).total * sizeof(float);
   if (!p.resident) {
     ELG_REQUIRE(N1 <= N_STREAM_MAX, ELG_EUNSUPPORTED, "rollout supports up to %d nodes (got %d)", N_STREAM_MAX, N1);
     p.smem = (size_t)make_layout(N1, p.MT, p.maxe * 8, false).total * sizeof(float);
@@ -1084,7 +1090,6 @@ static int launch_rollout(const elg_model_desc* d, RolloutArgs& a, cudaStream_t 
   return ELG_OK;
 }
 
-bool rollout_is_resident(int N1) { return N1 <= N_RES_MAX; }
 
 }  // namespace elg
 

@@ -113,9 +113,9 @@ class EncodedBatch:
         self.enc = torch.empty((B, N1, 128), dtype=f32, device=dev)
         self.k, self.v, self.qtab = big[0], big[1], big[2]
         self.qfirst = big[3] if handle.problem == "tsp" else None
-        self.e = torch.empty(int(lib.elg_e_bytes(B, N1)), dtype=torch.uint8, device=dev)
+        self.e = torch.empty(int(lib.elg_e_bytes(handle.desc, B, N1)), dtype=torch.uint8, device=dev)
         self.eb = torch.empty((B, N1), dtype=f32, device=dev)
-        self.nbr = torch.empty(int(lib.elg_nbr_bytes(ELG_CVRP if handle.problem == "cvrp" else ELG_TSP, B, N1)),
+        self.nbr = torch.empty(int(lib.elg_nbr_bytes(handle.desc, B, N1)),
                                dtype=torch.uint8, device=dev)
         self._big = big
         self.tables = _lib.Tables(*[_ptr(x).value for x in (self.xy, self.demand, self.unscaled, self.enc, self.k, self.v,

@@ -99,19 +99,19 @@ typedef struct elg_tables {
   float* k;               /* [B][N1][E]   decoder keys, pre-scaled by log2(e)/sqrt(qkv)          */
   float* v;               /* [B][N1][E]   decoder values                                         */
   void* e;                /* score matrix E' = enc * Wo-fold / sqrt(E); elg_e_bytes() per batch:
-                             N1 <= ELG_MAX_NODES_RESIDENT: fp16 hi/lo tcgen05 operand layout [B][2][E/8][N1p][8]
+                             resident variant: fp16 hi/lo tcgen05 operand layout [B][2][E/8][N1p][8]
                              larger:                       fp32 [B][N1][E], 16-byte chunks XOR-swizzled by (j & 7)  */
   float* eb;              /* [B][N1]      score bias    enc . bo / sqrt(E)                       */
   float* qtab;            /* [B][N1][E]   per-node last-node query  Wq_last[:, :E] * enc         */
   float* qfirst;          /* [B][N1][E]   tsp: per-node first-node query; NULL for cvrp          */
   void* nbr;              /* neighbour lists sorted by (distance, index); elg_nbr_bytes() per batch:
-                             N1 <= ELG_MAX_NODES_RESIDENT: uint8 [B][N1][ELG_NBR_STRIDE], 8-way interleaved
+                             resident variant (elg_rollout_resident() == 1): uint8 [B][N1][ELG_NBR_STRIDE], 8-way interleaved
                              larger:                       uint16 [B][N1][ELG_NBR16_STRIDE(NL)], rank order  */
 } elg_tables;
 
 #define ELG_NBR_STRIDE 128                          /* bytes per node, resident variant               */
 #define ELG_NBR16_STRIDE(NL) (((NL) + 63) & ~63)    /* uint16 entries per node, streaming variant     */
-#define ELG_MAX_NODES_RESIDENT 112                  /* K/V/E' stay in shared memory up to this size   */
+#define ELG_MAX_NODES_RESIDENT 112                  /* upper bound of the resident variant (also needs to fit smem) */
 #define ELG_MAX_NODES 8192                          /* largest instance the rollout supports          */
 #define ELG_MASK_WORDS(N1) (((N1) + 31) / 32)       /* uint32 words per row of every bit mask         */
 
@@ -160,10 +160,11 @@ int elg_encode(const elg_model_desc* desc, const float* weights, const float* de
  *   logp [B][M]          sample mode: sum of log-probabilities of the sampled actions (may be NULL)
  *   work_counter         one zero-initialised int32 (dynamic CTA scheduler)
  * elg_rollout_tiles() returns the number of row tiles per aug-instance used for (B, M, N1);
- * elg_nbr_bytes() the size of elg_tables.nbr.  Sampling mode needs N1 <= 128. */
+ * elg_nbr_bytes() / elg_e_bytes() the sizes of elg_tables.nbr / .e.  Sampling mode needs N1 <= 128. */
 int elg_rollout_tiles(const elg_model_desc* desc, int B, int M, int N1);
-size_t elg_nbr_bytes(int problem, int B, int N1);
-size_t elg_e_bytes(int B, int N1);
+int elg_rollout_resident(const elg_model_desc* desc, int N1);   /* 1 = resident variant, 0 = streaming, <0 = error */
+size_t elg_nbr_bytes(const elg_model_desc* desc, int B, int N1);
+size_t elg_e_bytes(const elg_model_desc* desc, int B, int N1);
 int elg_rollout(const elg_model_desc* desc, const float* derived, const elg_tables* t, int B, int M, int N1,
                 const int32_t* start_nodes, int mode, uint64_t seed, int t_max, int16_t* tours, float* reward,
                 int32_t* n_steps, float* logp, int32_t* work_counter, void* stream);

@@ -1,0 +1,70 @@
+"""Edge cases of the CUDA path: tiny / ragged shapes against the oracle, and loud failures outside the envelope."""
+import pytest
+import torch
+
+from helpers import compare_tours
+from oracle import elg_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(kind, N, M, n, aug, gain=3.0, seed=1):
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    sd = synthetic_state_dict(kind, seed=100 + seed, gain=gain)
+    W = O.Weights(sd, kind, mp)
+    if kind == "cvrp":
+        b = synthetic_cvrp_batch(n, N, seed=seed)
+        prob = O.load_cvrp(b["depot"], b["loc"], b["demand"], aug)
+    else:
+        prob = O.load_tsp(synthetic_tsp_batch(n, N, seed=seed), aug)
+    perm = O.start_permutation(kind, N, M, seed=seed)
+    ref_t, _, ref_r = O.rollout(W, prob, M, perm, "greedy")
+    handle = engine.ModelHandle(kind, mp, sd, DEV)
+    batch = engine.encode(handle, prob.xy.to(DEV), None if prob.demand is None else prob.demand.to(DEV))
+    tours16, reward, _, n_steps = engine.rollout(batch, M, perm.tolist())
+    T = int(n_steps.max())
+    return tours16[:, :, :T].long().cpu(), reward.cpu(), ref_t, ref_r, prob
+
+
+@pytest.mark.parametrize("kind,N,M,n,aug", [
+    ("cvrp", 5, 1, 3, 1),       # one POMO row, tiny instance (local neighbourhood smaller than k)
+    ("cvrp", 7, 5, 2, 8),       # M not a multiple of 4
+    ("cvrp", 45, 45, 1, 8),     # k = 40 < N: neighbour list truncation
+    ("cvrp", 111, 9, 1, 1),     # largest resident instance (N+1 = 112)
+    ("cvrp", 112, 9, 1, 1),     # smallest streaming instance (N+1 = 113)
+    ("tsp", 4, 4, 2, 1),
+    ("tsp", 31, 31, 1, 8),      # k = 30 = N-1
+    ("tsp", 112, 7, 1, 1),      # resident limit
+    ("tsp", 113, 7, 1, 1),      # streaming
+    ("tsp", 129, 129, 1, 1),    # 5 mask words, M > 128
+])
+def test_ragged_shapes_match_oracle(kind, N, M, n, aug):
+    tours, reward, ref_t, ref_r, prob = _run(kind, N, M, n, aug)
+    frac, same = compare_tours(tours, ref_t)
+    assert frac >= 0.9, frac
+    assert ((reward - ref_r).abs() / ref_r.abs())[same].max() < 1e-4
+    if kind == "cvrp":
+        O.check_feasible_cvrp(tours, prob.demand)
+    else:
+        assert torch.equal(tours.sort(dim=2)[0], torch.arange(N).expand_as(tours))
+
+
+def test_out_of_envelope_fails_loudly():
+    from elg_b200 import _lib, engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
+    mp = dict(DEFAULT_MODEL_PARAMS["tsp"])
+    handle = engine.ModelHandle("tsp", mp, synthetic_state_dict("tsp"), DEV)
+    xy = torch.rand(1, 130, 2, device=DEV)
+    batch = engine.encode(handle, xy)
+    with pytest.raises(_lib.ElgError):                                   # sampling is limited to 128 nodes
+        engine.rollout(batch, 8, list(range(8)), mode="sample")
+    with pytest.raises(ValueError):
+        engine.rollout(batch, 8, list(range(7)))                          # wrong start-node count
+    with pytest.raises(_lib.ElgError):
+        engine.encode(handle, torch.rand(1, 20, 2))                       # CPU tensor: no CPU path
+    big = torch.rand(1, 8200, 2, device=DEV)
+    with pytest.raises(_lib.ElgError):                                   # beyond ELG_MAX_NODES
+        engine.rollout(engine.encode(handle, big), 4, [0, 1, 2, 3])
