@@ -33,6 +33,9 @@ N_NODES, POMO, AUG = 100, 100, 8
 WEIGHT_SEED, INSTANCE_SEED = 1234, 1234
 ALG_BYTES_PER_AUG_STEP = 161548        # K+V+enc re-read + node statics + row state, CVRP100
 ALG_FLOP_PER_ROW_STEP = 329088         # reference arithmetic per decode row-step, CVRP100
+# dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the ncu --set full capture
+# (profiles/r01_rollout_v3_ncu.md: 124.4 MB for a 480-aug-instance launch): the decoder tables are read once per rollout
+NCU_DRAM_BYTES_PER_AUG_INSTANCE = 124.4e6 / 480
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -259,7 +262,10 @@ def run_ours(args):
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": {"kernel": "rollout_kernel<CVRP> (decode step + env step, whole rollout in one launch)",
                          "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None,
+                         "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src,
+                         "traffic": NCU_DRAM_BYTES_PER_AUG_INSTANCE * nb * AUG,
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_rollout_v3_ncu.md",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_AUG_STEP * aug_steps / max(len(events), 1),
                          "algorithmic_bytes_per_aug_instance_step": ALG_BYTES_PER_AUG_STEP,
                          "aug_instance_steps_per_launch": aug_steps / max(len(events), 1),
                          "kernel_ms_per_launch": k_ms / max(len(events), 1),
