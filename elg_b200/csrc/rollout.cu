@@ -318,7 +318,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             r = act ? full_blocks * 32 + pi % tail : 0;
           }
           act = act && !sFin[r];
-          float q[D], o[D];
+          // q and o live as float2 pairs: the dot products and the p.V update run on packed FFMA2 (sm_100
+          // fma.rn.f32x2: two IEEE fp32 FMAs per instruction, half the issue slots of scalar FFMA)
+          float2 q2[D / 2], o2[D / 2];
           if (act) {
             const int cur = sCur[r];
             const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + h * D);
@@ -334,14 +336,15 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
                 float4 f4 = __ldg(reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + sFirst[r]) * E + h * D) + d4);
                 v4.x = f4.x + v4.x; v4.y = f4.y + v4.y; v4.z = f4.z + v4.z; v4.w = f4.w + v4.w;
               }
-              q[d4 * 4] = v4.x; q[d4 * 4 + 1] = v4.y; q[d4 * 4 + 2] = v4.z; q[d4 * 4 + 3] = v4.w;
+              q2[d4 * 2] = make_float2(v4.x, v4.y);
+              q2[d4 * 2 + 1] = make_float2(v4.z, v4.w);
             }
           } else {
 #pragma unroll
-            for (int d = 0; d < D; ++d) q[d] = 0.f;
+            for (int d = 0; d < D / 2; ++d) q2[d] = make_float2(0.f, 0.f);
           }
 #pragma unroll
-          for (int d = 0; d < D; ++d) o[d] = 0.f;
+          for (int d = 0; d < D / 2; ++d) o2[d] = make_float2(0.f, 0.f);
           float m = -INFINITY, l = 0.f;
           const float* kp = pK + h * D;
           const float* vp = pV + h * D;
@@ -357,14 +360,14 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
               constexpr int NK = 4;
               int jb[NK];
               bool uu[NK];
-              float sc[NK];
+              float2 sc2[NK];
 #pragma unroll
               for (int n = 0; n < NK; ++n) {
                 const bool have = bits != 0;
                 jb[n] = have ? __ffs(bits) - 1 : jb[0];
                 uu[n] = have && !((mw >> jb[n]) & 1u);
                 bits &= bits - 1;
-                sc[n] = 0.f;
+                sc2[n] = make_float2(0.f, 0.f);
               }
 #pragma unroll
               for (int d4 = 0; d4 < D / 4; ++d4) {
@@ -372,18 +375,22 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
                 for (int n = 0; n < NK; ++n) {
                   const float4* kr = reinterpret_cast<const float4*>(kp + (size_t)(w * 32 + jb[n]) * E) + d4;
                   const float4 kk = RESIDENT ? *kr : __ldg(kr);
-                  sc[n] = fmaf(q[d4 * 4], kk.x, sc[n]); sc[n] = fmaf(q[d4 * 4 + 1], kk.y, sc[n]);
-                  sc[n] = fmaf(q[d4 * 4 + 2], kk.z, sc[n]); sc[n] = fmaf(q[d4 * 4 + 3], kk.w, sc[n]);
+                  sc2[n] = __ffma2_rn(q2[d4 * 2], make_float2(kk.x, kk.y), sc2[n]);
+                  sc2[n] = __ffma2_rn(q2[d4 * 2 + 1], make_float2(kk.z, kk.w), sc2[n]);
                 }
               }
+              float sc[NK];
               float smax = -INFINITY;
 #pragma unroll
-              for (int n = 0; n < NK; ++n) smax = fmaxf(smax, uu[n] ? sc[n] : -INFINITY);
+              for (int n = 0; n < NK; ++n) {
+                sc[n] = sc2[n].x + sc2[n].y;
+                smax = fmaxf(smax, uu[n] ? sc[n] : -INFINITY);
+              }
               if (smax > m + 12.f) {          // lazy rescale of the running softmax reference
                 const float c = exp2f(m - smax);
                 l *= c;
 #pragma unroll
-                for (int d = 0; d < D; ++d) o[d] *= c;
+                for (int d = 0; d < D / 2; ++d) o2[d] = __fmul2_rn(o2[d], make_float2(c, c));
                 m = smax;
               }
               float pp[NK];
@@ -396,8 +403,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
                   for (int n = 0; n < NK; ++n) {
                     const float4* vr = reinterpret_cast<const float4*>(vp + (size_t)(w * 32 + jb[n]) * E) + d4;
                     const float4 vv = RESIDENT ? *vr : __ldg(vr);
-                    o[d4 * 4] = fmaf(pp[n], vv.x, o[d4 * 4]); o[d4 * 4 + 1] = fmaf(pp[n], vv.y, o[d4 * 4 + 1]);
-                    o[d4 * 4 + 2] = fmaf(pp[n], vv.z, o[d4 * 4 + 2]); o[d4 * 4 + 3] = fmaf(pp[n], vv.w, o[d4 * 4 + 3]);
+                    const float2 p2 = make_float2(pp[n], pp[n]);
+                    o2[d4 * 2] = __ffma2_rn(p2, make_float2(vv.x, vv.y), o2[d4 * 2]);
+                    o2[d4 * 2 + 1] = __ffma2_rn(p2, make_float2(vv.z, vv.w), o2[d4 * 2 + 1]);
                   }
                 }
               }
@@ -405,6 +413,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           }
           if (act) {
             const float inv = 1.f / l;
+            float o[D];
+#pragma unroll
+            for (int d = 0; d < D / 2; ++d) { o[2 * d] = o2[d].x; o[2 * d + 1] = o2[d].y; }
             if (RESIDENT) {
               // fp16 hi/lo A operand of the score MMA: row r, columns h*16 .. h*16+15 = k-chunks 2h, 2h+1
               uint32_t hw[8], lw[8];
