@@ -25,48 +25,9 @@
 //            lane) against E', 128 nodes at a time.  B3: clip*tanh(score + penalty + local) + mask,
 //            running first-max argmax (or Philox sampling when N1 <= 128).
 //   phase C  env step on bit masks (fp32 load recurrence, visited / too-large masks by warp ballots).
-#include <string.h>
-#include "common.cuh"
-#include "umma.cuh"
+#include "rollout_common.cuh"
 
 namespace elg {
-
-constexpr int RW = 16;              // warps per CTA
-constexpr int RT = RW * 32;         // threads per CTA
-constexpr int MT_MAX = 64;          // rows per CTA
-constexpr int N_RES_MAX = 112;      // nodes the resident variant supports
-constexpr int N_STREAM_MAX = 8192;  // nodes the streaming variant supports (uint16 ids, sort kernel)
-constexpr int DS = 128;             // stride of the per-row dense penalty+local scratch (one node chunk)
-constexpr int TS = 36;              // padded row stride of the VPE / PE tables in smem
-constexpr int SS = 116;             // resident: row stride of the staged scores (112 scores + 4 neighbour-mask words)
-constexpr int A_HALF = 16384;       // resident: bytes of one fp16 A operand (64 rows x 128 k, K-major core matrices)
-constexpr unsigned FULL = 0xffffffffu;
-
-struct RolloutArgs {
-  elg_tables t;
-  const float* derived;
-  int problem, B, M, N1, MT, tiles, k_local;
-  float xi, clip;
-  const int32_t* start_nodes;
-  int mode;
-  unsigned long long seed;
-  int t_max;
-  int16_t* tours;
-  float* reward;
-  int32_t* n_steps;
-  float* logp;
-  int32_t* work_counter;
-  // single decode step from caller-provided state (model.one_step_rollout)
-  int single_step;
-  unsigned long long step_id;
-  const int32_t* st_cur;
-  const float* st_load;
-  const int32_t* st_first;
-  const uint32_t* st_mask;
-  int32_t* out_selected;
-  float* out_prob;
-  float* out_logits;
-};
 
 // ---- shared-memory layout (offsets in floats) ---------------------------------------------------
 struct SmemLayout {
@@ -113,53 +74,6 @@ __host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT, bool r
   L.bar = o; o += 8;                                // TMA mbarrier, MMA mbarrier, TMEM base address
   L.total = o;
   return L;
-}
-
-// ---- small PTX helpers --------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared (1D), completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// Philox4x32-10 (counter-based RNG for the sampling mode)
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
-
-__device__ __forceinline__ float octet_max(float v) {
-  v = fmaxf(v, __shfl_xor_sync(FULL, v, 1));
-  v = fmaxf(v, __shfl_xor_sync(FULL, v, 2));
-  return fmaxf(v, __shfl_xor_sync(FULL, v, 4));
-}
-__device__ __forceinline__ float octet_sum(float v) {
-  v += __shfl_xor_sync(FULL, v, 1);
-  v += __shfl_xor_sync(FULL, v, 2);
-  return v + __shfl_xor_sync(FULL, v, 4);
 }
 
 // =================================================================================================
@@ -229,6 +143,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 
   const int total_work = A.B * A.tiles;
   uint32_t bar_phase = 0, mma_phase = 0;
+#ifdef ELG_PHASE_TIMING
+  unsigned long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   const float sqrt_le = 5.656854249492381f;   // sqrt(32), used as a divisor like the reference
 
   for (int iter = 0;; ++iter) {
@@ -302,6 +219,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
     int t = 0;
     for (;; ++t) {
       const bool forced = !A.single_step && (t < 1 + DEP);
+      PHASE_T0();
       if (!forced) {
         // ================= phase A: multi-head attention, thread = (row, head) ====================
         const int full_blocks = nrows >> 5, tail = nrows & 31;
@@ -441,7 +359,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           }
         }
         if (RESIDENT) umma::fence_async_smem();     // generic-proxy operand writes -> tensor-core reads
+        PHASE_MARK(0);
         __syncthreads();
+        PHASE_MARK(1);
         if (RESIDENT && tid == 0) {
           // scores D[row][node] = o . E'  as  A_hi B_hi + A_hi B_lo + A_lo B_hi  (tcgen05, fp32 accumulate in TMEM)
           umma::fence_after_sync();
@@ -655,6 +575,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
         }
       }
 
+      PHASE_MARK(2);
       if (RESIDENT && !forced) {
         // ---- scores TMEM -> shared memory (+ eb): warps of TMEM lane quadrants 0/1 (rows 0..63), 4 column parts --
         if ((warp & 3) < 2) {
@@ -681,7 +602,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           umma::fence_before_sync();
         }
         mma_phase ^= 1;
+        PHASE_MARK(3);
         __syncthreads();
+        PHASE_MARK(4);
       }
 
       if (own) {
@@ -986,9 +909,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           }
         }
       }
+      PHASE_MARK(5);
       if (A.single_step) break;
       // ---- all rows finished?  (the barrier also publishes the new row state to phase A) ---------
       bool more = __syncthreads_or(warp_live) != 0;
+      PHASE_MARK(6);
       if (!CVRP) more = (t + 1) < N1;
       if (!more || t + 1 >= A.t_max) { ++t; break; }
     }
@@ -1019,6 +944,10 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem_d, 256);
   }
+#ifdef ELG_PHASE_TIMING
+  if (tid == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_clk[i], pclk[i]);
+#endif
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -1107,6 +1036,14 @@ static int launch_rollout(const elg_model_desc* d, RolloutArgs& a, cudaStream_t 
 using namespace elg;
 
 extern "C" {
+
+#ifdef ELG_PHASE_TIMING
+int elg_debug_phase_clocks(unsigned long long* out8, int reset) {
+  ELG_CUDA_OK(cudaMemcpyFromSymbol(out8, g_phase_clk, sizeof(unsigned long long) * 8));
+  if (reset) { unsigned long long z[8] = {0}; ELG_CUDA_OK(cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z))); }
+  return ELG_OK;
+}
+#endif
 
 int elg_rollout_tiles(const elg_model_desc* d, int B, int M, int N1) {
   if (check_desc(d) || M <= 0 || B <= 0) return -1;

@@ -38,20 +38,54 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
     *reinterpret_cast<__half*>(bLo + umma::elem_off(r, k, lboB)) = lo;
   }
   umma::fence_async_smem();
-  if (warp == 0) umma::tmem_alloc(tptr, 256);
+  if (warp == 0) umma::tmem_alloc(tptr, 512);
   if (tid == 0) umma::mbar_init(bar, 1);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = *tptr;
 
-  if (tid == 0) {
+  const bool ts_mode = terms == 6;
+  if (ts_mode) {
+    // A operand into tensor memory: thread = lane = row; hi at columns [256, 256+K/2), lo at [320, 320+K/2)
+    const int row = warp * 32 + lane;
+    for (int c8 = 0; c8 < K / 16; ++c8) {
+      uint32_t hw[8], lw[8];
+      for (int i = 0; i < 8; ++i) {
+        const int k = c8 * 16 + 2 * i;
+        __half h0 = __float2half_rn(0.f), l0 = h0, h1 = h0, l1 = h0;
+        if (row < rowsA) { umma::split_f16(A[(size_t)row * K + k], h0, l0); umma::split_f16(A[(size_t)row * K + k + 1], h1, l1); }
+        hw[i] = umma::pack_h2(h0, h1);
+        lw[i] = umma::pack_h2(l0, l1);
+      }
+      umma::st8(tbase + ((uint32_t)(warp * 32) << 16) + 256 + c8 * 8, hw);
+      umma::st8(tbase + ((uint32_t)(warp * 32) << 16) + 320 + c8 * 8, lw);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
+  if (tid == 0 && ts_mode) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N);
+    for (int term = 0; term < 3; ++term) {
+      const uint8_t* b = term == 1 ? bLo : bHi;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t bd = umma::make_desc(umma::smem_addr(b) + ks * 2 * lboB, lboB, 128);
+        umma::mma_f16_ts(tbase + (term ? 128u : 0u), tbase + (term == 2 ? 320u : 256u) + ks * 8, bd, idesc, !(ks == 0 && term <= 1));
+      }
+    }
+    umma::commit(bar);
+  }
+  if (tid == 0 && !ts_mode) {
     const uint32_t idesc = umma::make_idesc_f16(128, N);
     // terms == 5: hi*hi into accumulator 0, the two cross terms into accumulator 1 (columns 128..), summed on read-out
     const bool split_acc = terms == 5;
-    const int nterms = split_acc ? 3 : terms;
+    const bool cross_first = terms == 7;
+    const int nterms = (split_acc || cross_first) ? 3 : terms;
     bool acc = false;
-    for (int term = 0; term < nterms; ++term) {
+    for (int it = 0; it < nterms; ++it) {
+      const int term = cross_first ? (it == 2 ? 0 : it + 1) : it;      // cross_first: hi*lo, lo*hi, then hi*hi
       if (split_acc && term == 1) acc = false;
       const uint8_t* a = term >= 2 ? aLo : aHi;
       const uint8_t* b = (term == 1 || term == 3) ? bLo : bHi;
@@ -69,7 +103,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   for (int c = 0; c < N; c += 16) {
     float v[16];
     umma::ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
-    if (terms == 5) {
+    if (terms == 5 || terms == 6) {
       float v2[16];
       umma::ld16(tbase + ((uint32_t)(warp * 32) << 16) + 128 + c, v2);
       for (int i = 0; i < 16; ++i) v[i] += v2[i];
@@ -78,7 +112,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
 }  // namespace elg
@@ -89,7 +123,7 @@ extern "C" int elg_selftest_umma(const float* a, const float* b, float* d, int r
                                  void* stream) {
   ELG_REQUIRE(a && b && d, ELG_EINVAL, "NULL pointer");
   ELG_REQUIRE(n % 16 == 0 && n >= 16 && n <= 128 && k % 16 == 0 && k >= 16 && k <= 128, ELG_EINVAL, "need N,K multiples of 16 in [16,128]");
-  ELG_REQUIRE(rows_a >= 1 && rows_a <= (alias ? 64 : 128) && terms >= 1 && terms <= 5, ELG_EINVAL, "bad rows/terms");
+  ELG_REQUIRE(rows_a >= 1 && rows_a <= (alias ? 64 : 128) && terms >= 1 && terms <= 7, ELG_EINVAL, "bad rows/terms");
   const int chunks = k / 8;
   const size_t sizeA = (size_t)chunks * (alias ? 64 : 128) * 16 + (alias ? 1024 : 0), sizeB = (size_t)chunks * n * 16;
   const size_t smem = 2 * sizeA + 2 * sizeB + 64;

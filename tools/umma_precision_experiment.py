@@ -30,3 +30,11 @@ rep('umma hi*hi | cross terms separate', run(a, b, 5))
 a3 = torch.randn(100, 128, generator=g).cuda() * 3; b3 = torch.randn(112, 128, generator=g).cuda() * 0.3
 ref = a3.double() @ b3.double().T; scale = ref.abs().mean()
 rep('other data: fp32 matmul', (a3 @ b3.T).double()); rep('other data: umma 3 terms', run(a3, b3, 3)); rep('other data: umma split acc', run(a3, b3, 5))
+print('--- A operand in tensor memory (tcgen05.mma TS form, terms=6) ---')
+rep('other data: umma TS split acc', run(a3, b3, 6))
+ref = a.double() @ b.double().T; scale = ref.abs().mean()
+rep('first data: umma TS split acc', run(a, b, 6))
+print('--- single accumulator, cross terms issued first, hi*hi last (terms=7) ---')
+rep('first data: cross-first single acc', run(a, b, 7))
+ref = a3.double() @ b3.double().T; scale = ref.abs().mean()
+rep('other data: cross-first single acc', run(a3, b3, 7))
