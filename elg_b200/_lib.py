@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libelg_b200.so")
 ELG_TSP, ELG_CVRP = 0, 1
 ELG_GREEDY, ELG_SAMPLE = 0, 1
 FLAG_ENSEMBLE, FLAG_DISTANCE_PENALTY, FLAG_POSITIONAL = 1, 2, 4
+FLAG_ATTN_FP32, FLAG_ATTN_TENSOR = 8, 16
 MAX_LAYERS = 16
 NBR_STRIDE = 128
 ABI_VERSION = 1

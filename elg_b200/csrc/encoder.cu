@@ -134,11 +134,11 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
         }
         if (EPI == EPI_UMMA_SPLIT) {
           // fp16 hi/lo halves in the K-major core-matrix layout the rollout kernel feeds to tcgen05 (umma.cuh):
-          // per aug-instance [hi | lo], each N1p rows x 128 k; element (j, k) at (k/8)*N1p*16 + (j/8)*128 + (j%8)*16 + (k%8)*2
+          // per aug-instance 3 operands [E' | K' | V^T] of N1p*512 bytes; this epilogue writes E' = [hi | lo], each N1p rows x 128 k; element (j, k) at (k/8)*N1p*16 + (j/8)*128 + (j%8)*16 + (k%8)*2
           const int N1p = (N1 + 15) & ~15;
           const long long bi = m / N1;
           const int j = (int)(m % N1);
-          uint8_t* base = reinterpret_cast<uint8_t*>(C) + bi * ((long long)N1p * 512) + (size_t)(n >> 3) * N1p * 16 +
+          uint8_t* base = reinterpret_cast<uint8_t*>(C) + bi * (3LL * N1p * 512) + (size_t)(n >> 3) * N1p * 16 +
                           (j >> 3) * 128 + (j & 7) * 16 + (n & 7) * 2;
           const float vv[4] = {v.x, v.y, v.z, v.w};
           __half hi[4], lo[4];
@@ -161,6 +161,43 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
     }
 }
 
+
+// ---- decoder keys / values as fp16 hi/lo tcgen05 B operands (rollout_tc.cu), segments 1 and 2 of elg_tables.e ----
+//   K'  [N1p keys x 128 k]  element (j, c) at (c/8)*N1p*16 + (j/8)*128 + (j%8)*16 + (c%8)*2        (like E')
+//   V^T per head h: [16 d x N1p keys]  element (d, j) at h*N1p*32 + (j/8)*256 + (d/8)*128 + (d%8)*16 + (j%8)*2
+// each as [hi | lo] halves of N1p*256 bytes.  One CTA per aug-instance; padded keys stay zero (memset by the caller).
+__global__ void __launch_bounds__(256) split_kv_kernel(const float* __restrict__ K, const float* __restrict__ V,
+                                                       uint8_t* __restrict__ ops, int N1) {
+  const int N1p = (N1 + 15) & ~15;
+  const size_t b = blockIdx.x;
+  const float* kp = K + b * N1 * E;
+  const float* vp = V + b * N1 * E;
+  uint8_t* ko = ops + b * 3 * ((size_t)N1p * 512) + (size_t)N1p * 512;
+  uint8_t* vo = ko + (size_t)N1p * 512;
+  const uint32_t half = (uint32_t)N1p * 256u;
+  for (int i = threadIdx.x; i < N1 * (E / 2); i += 256) {        // K': column pairs of one key -> one 32-bit word
+    const int j = i / (E / 2), c = (i % (E / 2)) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(kp + (size_t)j * E + c);
+    __half h0, l0, h1, l1;
+    umma::split_f16(v.x, h0, l0);
+    umma::split_f16(v.y, h1, l1);
+    const uint32_t off = umma::elem_off(j, c, (uint32_t)N1p * 16u);
+    *reinterpret_cast<uint32_t*>(ko + off) = umma::pack_h2(h0, h1);
+    *reinterpret_cast<uint32_t*>(ko + half + off) = umma::pack_h2(l0, l1);
+  }
+  const int jp = (N1 + 1) >> 1;
+  for (int i = threadIdx.x; i < jp * E; i += 256) {               // V^T: key pairs of one (head, d) -> one 32-bit word
+    const int c = i % E, j = (i / E) * 2;
+    const float a = vp[(size_t)j * E + c];
+    const float bq = j + 1 < N1 ? vp[(size_t)(j + 1) * E + c] : 0.f;
+    __half h0, l0, h1, l1;
+    umma::split_f16(a, h0, l0);
+    umma::split_f16(bq, h1, l1);
+    const uint32_t off = (uint32_t)(c >> 4) * (uint32_t)N1p * 32u + umma::elem_off(c & 15, j, 256u);
+    *reinterpret_cast<uint32_t*>(vo + off) = umma::pack_h2(h0, h1);
+    *reinterpret_cast<uint32_t*>(vo + half + off) = umma::pack_h2(l0, l1);
+  }
+}
 
 // ---- tcgen05 GEMM  C[M][N] = A[M][K] * W[N][K]^T (+ bias / relu / residual) ---------------------------------
 // Split precision: x = hi + lo (fp16 pair, ~22 mantissa bits); D = A_hi W_hi + A_hi W_lo + A_lo W_hi accumulated in
@@ -486,6 +523,8 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
   if (rollout_is_resident(d, N1)) {
     ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(d, B, N1), st));      // padded rows of the MMA operand must be zero
     ELG_TRY(gemm<EPI_UMMA_SPLIT>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
+    split_kv_kernel<<<(unsigned)B, 256, 0, st>>>(t->k, t->v, reinterpret_cast<uint8_t*>(t->e), N1);
+    ELG_LAUNCH_OK();
   } else {
     ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
   }

@@ -254,7 +254,7 @@ int elg_rollout_resident(const elg_model_desc* d, int N1) {
 
 size_t elg_e_bytes(const elg_model_desc* d, int B, int N1) {
   if (check_desc(d) || B <= 0 || N1 <= 1) return 0;
-  if (rollout_is_resident(d, N1)) return (size_t)B * ((N1 + 15) & ~15) * 512;     // fp16 hi + lo, rows padded to 16
+  if (rollout_is_resident(d, N1)) return (size_t)B * 3 * ((N1 + 15) & ~15) * 512;     // E' | K' | V^T, each fp16 hi + lo, rows padded to 16
   return (size_t)B * N1 * 128 * sizeof(float);
 }
 

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
         mbar_expect_tx(bar, 2 * bytes + ebytes);
         bulk_g2s(sK, A.t.k + (size_t)b * N1 * E, bytes, bar);
         bulk_g2s(sV, A.t.v + (size_t)b * N1 * E, bytes, bar);
-        bulk_g2s(sE, reinterpret_cast<const uint8_t*>(A.t.e) + (size_t)b * ebytes, ebytes, bar);
+        bulk_g2s(sE, reinterpret_cast<const uint8_t*>(A.t.e) + (size_t)b * 3 * ebytes, ebytes, bar);      // segment 0 of [E' | K' | V^T]
       }
       for (int i = tid; i < N1; i += RT) {
         sEb[i] = A.t.eb[(size_t)b * N1 + i];
@@ -997,7 +997,21 @@ static int make_plan(const elg_model_desc* d, int B, int M, int N1, Plan& p) {
   return ELG_OK;
 }
 
+int launch_rollout_tc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st);
+int rollout_tc_tiles(const elg_model_desc* d, int B, int M, int N1, int* mt_out);
+
+// Tensor-core attention kernel (rollout_tc.cu): resident instances, greedy decoding, and enough aug-instances that
+// whole-instance CTAs fill the machine -- or when forced by ELG_FLAG_ATTN_TENSOR; ELG_FLAG_ATTN_FP32 forces this file's kernel.
+static bool use_tensor_attention(const elg_model_desc* d, const RolloutArgs& a) {
+  if (a.mode != ELG_GREEDY || (d->flags & ELG_FLAG_ATTN_FP32) || !rollout_is_resident(d, a.N1)) return false;
+  const int tiles = rollout_tc_tiles(d, a.B, a.M, a.N1, nullptr);
+  if (tiles <= 0) return false;
+  if (d->flags & ELG_FLAG_ATTN_TENSOR) return true;
+  return false;      // automatic choice: the fp32-pipe kernel until the tensor-core kernel is the faster one
+}
+
 static int launch_rollout(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) {
+  if (use_tensor_attention(d, a)) return launch_rollout_tc(d, a, st);
   Plan p;
   int rc = make_plan(d, a.B, a.M, a.N1, p);
   if (rc) return rc;
@@ -1049,7 +1063,8 @@ int elg_rollout_tiles(const elg_model_desc* d, int B, int M, int N1) {
   if (check_desc(d) || M <= 0 || B <= 0) return -1;
   Plan p;
   if (make_plan(d, B, M, N1, p)) return -1;
-  return p.tiles;
+  const int tc = rollout_tc_tiles(d, B, M, N1, nullptr);      // the tensor-core kernel never uses more tiles
+  return p.tiles > tc ? p.tiles : tc;
 }
 
 static int fill_common(const elg_model_desc* d, const float* derived, const elg_tables* t, int B, int M, int N1,

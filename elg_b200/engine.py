@@ -5,6 +5,7 @@ libelg_b200.so.  Nothing in this module runs the path on the CPU: tensors must l
 CUDA device and the calls raise otherwise.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -75,12 +76,19 @@ def weight_slots(problem, desc):
 class ModelHandle:
     """Packed weights + folded tables of one model on one device."""
 
-    def __init__(self, problem, model_params, state_dict, device):
+    def __init__(self, problem, model_params, state_dict, device, attention=None):
+        """attention: None/"auto" (library chooses per shape), "tensor" (tcgen05 attention kernel whenever eligible) or
+        "fp32" (fp32-pipe attention kernel); default from the ELG_B200_ATTENTION environment variable.  Diagnostics only:
+        both kernels compute the same decode step."""
         self.problem, self.model_params = problem, dict(model_params)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.ElgError("elg_b200 needs a CUDA device (got %s); there is no CPU path" % device)
         self.desc = make_desc(problem, model_params)
+        attention = attention or os.environ.get("ELG_B200_ATTENTION", "auto")
+        if attention not in ("auto", "tensor", "fp32"):
+            raise ValueError("attention must be auto, tensor or fp32")
+        self.desc.flags |= {"auto": 0, "tensor": _lib.FLAG_ATTN_TENSOR, "fp32": _lib.FLAG_ATTN_FP32}[attention]
         slots, total = weight_slots(problem, self.desc)
         missing = [k for k in slots if k not in state_dict]
         if missing:

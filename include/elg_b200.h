@@ -36,7 +36,10 @@ enum { ELG_GREEDY = 0, ELG_SAMPLE = 1 };
 enum {
   ELG_FLAG_ENSEMBLE = 1,          /* model_params['ensemble']          */
   ELG_FLAG_DISTANCE_PENALTY = 2,  /* model_params['distance_penalty']  */
-  ELG_FLAG_POSITIONAL = 4         /* model_params['positional']        */
+  ELG_FLAG_POSITIONAL = 4,        /* model_params['positional']        */
+  /* kernel selection for elg_rollout / elg_decode_step (diagnostics; default = automatic) */
+  ELG_FLAG_ATTN_FP32 = 8,         /* always the fp32-pipe attention kernel (rollout.cu)                     */
+  ELG_FLAG_ATTN_TENSOR = 16       /* tensor-core attention kernel (rollout_tc.cu) whenever it is eligible   */
 };
 enum {
   ELG_OK = 0,
@@ -99,7 +102,8 @@ typedef struct elg_tables {
   float* k;               /* [B][N1][E]   decoder keys, pre-scaled by log2(e)/sqrt(qkv)          */
   float* v;               /* [B][N1][E]   decoder values                                         */
   void* e;                /* score matrix E' = enc * Wo-fold / sqrt(E); elg_e_bytes() per batch:
-                             resident variant: fp16 hi/lo tcgen05 operand layout [B][2][E/8][N1p][8]
+                             resident variant: three fp16 hi/lo tcgen05 B operands per aug-instance,
+                                               [B][E' | K' | V^T][2][..], N1p*512 bytes each (N1p = N1 rounded up to 16)
                              larger:                       fp32 [B][N1][E], 16-byte chunks XOR-swizzled by (j & 7)  */
   float* eb;              /* [B][N1]      score bias    enc . bo / sqrt(E)                       */
   float* qtab;            /* [B][N1][E]   per-node last-node query  Wq_last[:, :E] * enc         */

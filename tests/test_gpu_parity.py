@@ -20,9 +20,9 @@ LOGIT_MAX_ATOL = 2e-3
 LOGIT_MEAN_ATOL = 3e-5
 
 
-def _setup(g):
+def _setup(g, attention="fp32"):
     from elg_b200 import engine
-    handle = engine.ModelHandle(g.kind, g.model_params(), g.state_dict(), DEV)
+    handle = engine.ModelHandle(g.kind, g.model_params(), g.state_dict(), DEV, attention=attention)
     prob = g.oracle_problem()
     xy = prob.xy.to(DEV)
     dem = None if prob.demand is None else prob.demand.to(DEV)
@@ -30,10 +30,21 @@ def _setup(g):
     return engine, handle, prob, batch
 
 
-@pytest.fixture(scope="module", params=ALL_CASES)
+def _case_params():
+    """Every fixture on the fp32-pipe attention kernel; the resident ones (N+1 <= 112) also on the tensor-core kernel."""
+    out = []
+    for name in ALL_CASES:
+        out.append((name, "fp32"))
+        g = Golden(name)
+        if g.meta["N"] + (1 if g.kind == "cvrp" else 0) <= 112:
+            out.append((name, "tensor"))
+    return out
+
+
+@pytest.fixture(scope="module", params=_case_params(), ids=lambda p: "%s-%s" % p)
 def case(request):
-    g = Golden(request.param)
-    return (g,) + _setup(g)
+    g = Golden(request.param[0])
+    return (g,) + _setup(g, request.param[1])
 
 
 def test_encoder_matches_reference(case):

@@ -20,9 +20,11 @@ from elg_b200.cvrp import CVRPEnv, CVRPModel
 from elg_b200.cvrp.test import solve_batch
 from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
 
-NAMES = sys.argv[1:] or ["A", "A-barrier", "B1", "copy", "copy-barrier", "B3+C", "end-barrier", "-"]
+TC = os.environ.get("ELG_B200_ATTENTION") == "tensor"
+NAMES = (["Q build", "softmax+P (4 rounds)", "B1 (2 passes)", "O operand", "B3", "select+C", "end barrier", "-"] if TC else
+         ["A", "A-barrier", "B1", "copy", "copy-barrier", "B3+C", "end-barrier", "-"])
 dev = "cuda:0"
-fn = _lib.lib.elg_debug_phase_clocks
+fn = _lib.lib.elg_debug_phase_clocks_tc if TC else _lib.lib.elg_debug_phase_clocks
 model = CVRPModel(**dict(DEFAULT_MODEL_PARAMS["cvrp"]))
 model.decoder.add_local_policy(dev)
 model.load_state_dict(synthetic_state_dict("cvrp", seed=1234))
