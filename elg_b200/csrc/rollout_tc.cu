@@ -12,16 +12,18 @@
 //
 // CTA = one (aug-instance, tile of <= 112 POMO rows); TMEM lane = row.  16 warps: warp w owns TMEM lane quadrant
 // q = w % 4 (rows 32q..32q+31) and sub-slot wsub = w / 4:
-//   softmax  thread = (row, head-of-round hh = wsub & 1, key half kh = wsub >> 1); 4 rounds of 2 heads; the two key
-//            halves of a (row, head) exchange (max, sum) through shared memory + a 64-thread named barrier
-//   B1       local policy, octet of lanes per row exactly as in rollout.cu (two passes of 64 rows, run while the
-//            tensor core works on P.V / the next Q.K), results to shared memory ordered by node id
+//   softmax  two independent groups of 8 warps (grp = wsub / 2): group g walks heads 4g..4g+3 one at a time through
+//            its own S/P buffer, its own mbarrier and a 256-thread named barrier, so one group's tensor-core / TMEM
+//            latency is covered by the other group's arithmetic.  thread = (row, key half kh = wsub & 1); the two
+//            halves of a row exchange (max, sum) through shared memory + a 64-thread named barrier
+//   B1       local policy, octet of lanes per row exactly as in rollout.cu (4-row tasks dealt to the groups, run
+//            while the tensor core works on P.V / the next Q.K), results to shared memory ordered by node id
 //   B3       thread = (row, quarter wsub of the node columns): clip*tanh(score + eb + {penalty+local | xi}) + mask,
 //            first-max argmax combined across the 4 quarters through shared memory
 //   C        env step: every thread of a row recomputes the scalar state, owns mask word wsub
 //
 // TMEM columns: [0,128) Q hi|lo, later O hi|lo   [128,256) O accumulators (8 heads x 16)
-//               [256,256+2*N1p) S / P of the round's two heads, later the score accumulator
+//               [256,256+2*N1p) S / P buffers of the two groups, later the score accumulator
 #include "rollout_common.cuh"
 
 namespace elg {
@@ -68,7 +70,7 @@ __host__ __device__ inline TcLayout make_tc_layout(int N1, int MT, int KT, int K
   L.nb = o; o += MT * 4;                    // neighbour bit mask per row
   L.xch = o; o += 2 * 4 * 128;              // softmax (max, sum) exchange; later the 4 argmax candidates per row
   L.ctrl = o; o += 4;
-  L.bar = o; o += 8;
+  L.bar = o; o += 12;                       // 4 mbarriers + TMEM base address
   L.total = o;
   return L;
 }
@@ -77,6 +79,7 @@ __device__ __forceinline__ uint32_t pick4(const uint32_t (&w)[4], int i) {
   return i == 0 ? w[0] : (i == 1 ? w[1] : (i == 2 ? w[2] : (i == 3 ? w[3] : 0u)));
 }
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
 // =================================================================================================
 template <int PROBLEM, int MAXE>
@@ -118,11 +121,12 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
   float* sXl = sm + L.xch + 512;        // [4][128]
   int* sCtrl = reinterpret_cast<int*>(sm + L.ctrl);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);      // TMA completion
-  uint64_t* bar_mma = bar + 1;                                    // tcgen05.commit completion
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+  uint64_t* bar_sc = bar + 1;                                     // tcgen05.commit of the score MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, wsub = warp >> 2, hh = wsub & 1, kh = wsub >> 1;
+  const int q = warp & 3, wsub = warp >> 2, grp = wsub >> 1, kh = wsub & 1;     // softmax group (heads 4*grp..), key half
+  uint64_t* bar_grp = bar + 2 + grp;                              // tcgen05.commit of this softmax group's MMAs
   const int row = q * 32 + lane;                   // TMEM lane = row of the tile
   const int rc = row < A.MT ? row : 0;             // clamped index into the per-row state arrays
   const int KH = N1p >> 1, CQ = N1p >> 2;          // keys per softmax thread, node columns per B3 thread
@@ -143,7 +147,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
     for (int i = tid; i < LE * LE; i += RT) w[L.wct + i] = loc[LOC_WCT + i];
     if (tid == 0) {
       mbar_init(bar, 1);
-      mbar_init(bar_mma, 1);
+      mbar_init(bar + 1, 1);
+      mbar_init(bar + 2, 1);
+      mbar_init(bar + 3, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) umma::tmem_alloc(tmem_ptr, 512);
@@ -163,7 +169,8 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
   const int nks = N1p >> 4;
 
   const int total_work = A.B * A.tiles;
-  uint32_t bar_phase = 0, mma_phase = 0;
+  uint32_t bar_phase = 0, sc_phase = 0, grp_phase = 0;
+  const bool leader = tid == grp * 256;                           // issues this group's MMAs
   const float sqrt_le = 5.656854249492381f;
 #ifdef ELG_PHASE_TIMING
   unsigned long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         // ---- Q operand: q = Wq_last [enc[cur]; load] (cvrp) / q_first + Wq_last enc[cur] (tsp), fp16 hi/lo -> TMEM ----
 #pragma unroll
         for (int i2 = 0; i2 < 2; ++i2) {
-          const int head = 4 * kh + 2 * i2 + hh;
+          const int head = 2 * wsub + i2;
           uint32_t hw[8], lw[8];
           if (act) {
             const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur0) * E + head * D);
@@ -265,11 +272,8 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
                 const float4 f4 = __ldg(reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + sFirst[rc]) * E + head * D) + d4);
                 v4.x = f4.x + v4.x; v4.y = f4.y + v4.y; v4.z = f4.z + v4.z; v4.w = f4.w + v4.w;
               }
-              __half h0, l0, h1, l1, h2, l2, h3, l3;
-              umma::split_f16(v4.x, h0, l0); umma::split_f16(v4.y, h1, l1);
-              umma::split_f16(v4.z, h2, l2); umma::split_f16(v4.w, h3, l3);
-              hw[d4 * 2] = umma::pack_h2(h0, h1); hw[d4 * 2 + 1] = umma::pack_h2(h2, h3);
-              lw[d4 * 2] = umma::pack_h2(l0, l1); lw[d4 * 2 + 1] = umma::pack_h2(l2, l3);
+              umma::split2_f16(v4.x, v4.y, hw[d4 * 2], lw[d4 * 2]);
+              umma::split2_f16(v4.z, v4.w, hw[d4 * 2 + 1], lw[d4 * 2 + 1]);
             }
           } else {
 #pragma unroll
@@ -283,38 +287,30 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         __syncthreads();
 
         // MMA issue helpers (thread 0 only).  Per contraction: lo*hi, hi*lo, then hi*hi into one accumulator.
-        auto issue_qk = [&](int rho) {
-#pragma unroll
-          for (int hx = 0; hx < 2; ++hx) {
-            const int head = 2 * rho + hx;
-            const uint32_t d = tm + TC_COL_S + hx * N1p;
-            const uint32_t aHi = tm + TC_COL_Q + 8 * head, aLo = aHi + 64;
-            const uint64_t bHi = umma::make_desc(opK + head * 2 * lboN, lboN, 128);
-            const uint64_t bLo = umma::make_desc(opK + half + head * 2 * lboN, lboN, 128);
-            umma::mma_f16_ts(d, aLo, bHi, idescS, false);
-            umma::mma_f16_ts(d, aHi, bLo, idescS, true);
-            umma::mma_f16_ts(d, aHi, bHi, idescS, true);
-          }
+        auto issue_qk = [&](int head) {
+          const uint32_t d = tm + TC_COL_S + grp * N1p;
+          const uint32_t aHi = tm + TC_COL_Q + 8 * head, aLo = aHi + 64;
+          const uint64_t bHi = umma::make_desc(opK + head * 2 * lboN, lboN, 128);
+          const uint64_t bLo = umma::make_desc(opK + half + head * 2 * lboN, lboN, 128);
+          umma::mma_f16_ts(d, aLo, bHi, idescS, false);
+          umma::mma_f16_ts(d, aHi, bLo, idescS, true);
+          umma::mma_f16_ts(d, aHi, bHi, idescS, true);
         };
-        auto issue_pv = [&](int rho) {
-#pragma unroll
-          for (int hx = 0; hx < 2; ++hx) {
-            const int head = 2 * rho + hx;
-            const uint32_t d = tm + TC_COL_O + 16 * head;
-            const uint32_t pHi = tm + TC_COL_S + hx * N1p, pLo = pHi + (N1p >> 1);
-            const uint32_t vHi = opV + head * (N1p * 32), vLo = vHi + half;
-            for (int ks = 0; ks < nks; ++ks)
-              umma::mma_f16_ts(d, pLo + 8 * ks, umma::make_desc(vHi + ks * 512, 256, 128), idescO, ks > 0);
-            for (int ks = 0; ks < nks; ++ks)
-              umma::mma_f16_ts(d, pHi + 8 * ks, umma::make_desc(vLo + ks * 512, 256, 128), idescO, true);
-            for (int ks = 0; ks < nks; ++ks)
-              umma::mma_f16_ts(d, pHi + 8 * ks, umma::make_desc(vHi + ks * 512, 256, 128), idescO, true);
-          }
+        auto issue_pv = [&](int head) {
+          const uint32_t d = tm + TC_COL_O + 16 * head;
+          const uint32_t pHi = tm + TC_COL_S + grp * N1p, pLo = pHi + (N1p >> 1);
+          const uint32_t vHi = opV + head * (N1p * 32), vLo = vHi + half;
+          for (int ks = 0; ks < nks; ++ks)
+            umma::mma_f16_ts(d, pLo + 8 * ks, umma::make_desc(vHi + ks * 512, 256, 128), idescO, ks > 0);
+          for (int ks = 0; ks < nks; ++ks)
+            umma::mma_f16_ts(d, pHi + 8 * ks, umma::make_desc(vLo + ks * 512, 256, 128), idescO, true);
+          for (int ks = 0; ks < nks; ++ks)
+            umma::mma_f16_ts(d, pHi + 8 * ks, umma::make_desc(vHi + ks * 512, 256, 128), idescO, true);
         };
-        if (tid == 0) {
+        if (leader) {
           umma::fence_after_sync();
-          issue_qk(0);
-          umma::commit(bar_mma);
+          issue_qk(4 * grp);
+          umma::commit(bar_grp);
         }
         PHASE_MARK(0);
 
@@ -325,14 +321,14 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           v0 = __funnelshift_r(pick4(inv, wd), pick4(inv, wd + 1), sh);
           v1 = __funnelshift_r(pick4(inv, wd + 1), pick4(inv, wd + 2), sh);
         }
-        float lt0 = 0.f, lt1 = 0.f, lt2 = 0.f, lt3 = 0.f;       // softmax denominators of head 2*rho + hh
+        float lt0 = 0.f, lt1 = 0.f, lt2 = 0.f, lt3 = 0.f;       // softmax denominators of heads 4*grp + rho
 
 #pragma unroll 1
         for (int rho = 0; rho < 4; ++rho) {
-          mbar_wait(bar_mma, mma_phase);
-          mma_phase ^= 1;
+          mbar_wait(bar_grp, grp_phase);
+          grp_phase ^= 1;
           umma::fence_after_sync();
-          const uint32_t sb = tl + TC_COL_S + hh * N1p;
+          const uint32_t sb = tl + TC_COL_S + grp * N1p;
           uint32_t sr[56];
 #pragma unroll
           for (int c8 = 0; c8 < 7; ++c8)
@@ -350,7 +346,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
                 mloc = fmaxf(mloc, s);
               }
             }
-          const float moff = mloc - TC_P_SCALE_LOG2;
+          const float moff = mloc == -INFINITY ? 0.f : mloc - TC_P_SCALE_LOG2;
           float lloc = 0.f;
 #pragma unroll
           for (int c8 = 0; c8 < 7; ++c8)
@@ -358,7 +354,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
 #pragma unroll
               for (int i = c8 * 8; i < c8 * 8 + 8; ++i) {
                 const float s = __uint_as_float(sr[i]);
-                const float p = s == -INFINITY ? 0.f : exp2f(s - moff);
+                const float p = umma::ex2_raw(s - moff);
                 lloc += p;
                 sr[i] = __float_as_uint(p);
               }
@@ -366,11 +362,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           // combine the two key halves of (row, head): common reference max, total denominator
           sXm[wsub * 128 + row] = mloc;
           sXl[wsub * 128 + row] = lloc;
-          pair_sync(1 + (warp & 7));
-          const float mo = sXm[(wsub ^ 2) * 128 + row], lo_ = sXl[(wsub ^ 2) * 128 + row];
+          pair_sync(1 + grp * 4 + q);
+          const float mo = sXm[(wsub ^ 1) * 128 + row], lo_ = sXl[(wsub ^ 1) * 128 + row];
           const float mm = fmaxf(mloc, mo);
-          const float cown = mloc == -INFINITY ? 0.f : exp2f(mloc - mm);
-          const float coth = mo == -INFINITY ? 0.f : exp2f(mo - mm);
+          const float cown = mloc == -INFINITY ? 0.f : umma::ex2_raw(mloc - mm);
+          const float coth = mo == -INFINITY ? 0.f : umma::ex2_raw(mo - mm);
           const float ltot = fmaf(lloc, cown, lo_ * coth);
           if (rho == 0) lt0 = ltot; else if (rho == 1) lt1 = ltot; else if (rho == 2) lt2 = ltot; else lt3 = ltot;
           // P (fp16 hi/lo, two keys per 32-bit column) in place of S: hi at [sb, sb + N1p/2), lo behind it
@@ -379,30 +375,26 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             if (c8 * 8 < KH) {
               uint32_t hw[4], lw[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __half h0, l0, h1, l1;
-                umma::split_f16(__uint_as_float(sr[c8 * 8 + 2 * i]) * cown, h0, l0);
-                umma::split_f16(__uint_as_float(sr[c8 * 8 + 2 * i + 1]) * cown, h1, l1);
-                hw[i] = umma::pack_h2(h0, h1);
-                lw[i] = umma::pack_h2(l0, l1);
-              }
+              for (int i = 0; i < 4; ++i)
+                umma::split2_f16(__uint_as_float(sr[c8 * 8 + 2 * i]) * cown, __uint_as_float(sr[c8 * 8 + 2 * i + 1]) * cown, hw[i], lw[i]);
               umma::st4(sb + kh * (KH >> 1) + c8 * 4, hw);
               umma::st4(sb + (N1p >> 1) + kh * (KH >> 1) + c8 * 4, lw);
             }
           umma::wait_st();
           umma::fence_before_sync();
-          __syncthreads();
-          if (tid == 0) {
+          group_sync(9 + grp);
+          if (leader) {
             umma::fence_after_sync();
-            issue_pv(rho);
-            if (rho < 3) issue_qk(rho + 1);
-            umma::commit(bar_mma);
+            issue_pv(4 * grp + rho);
+            if (rho < 3) issue_qk(4 * grp + rho + 1);
+            umma::commit(bar_grp);
           }
           PHASE_MARK(1);
 
           // ---- B1: local policy for rows [64 rho, 64 rho + 64), octet of lanes per row, while the tensor core runs ----
           if (rho < 2) {
-            const int r0 = rho * 64 + warp * 4;
+            // 4-row tasks dealt alternately to the two groups so both carry the same local-policy load
+            const int r0 = 4 * (((rho * 8 + kh * 4 + q) << 1) + grp);
             const bool own = r0 < nrows;
             const int rq = lane >> 3, s8 = lane & 7;
             const int myr = own ? min(r0 + rq, nrows - 1) : 0;
@@ -582,28 +574,24 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         }
 
         // ---- O = P V accumulated: normalise, fp16 hi/lo -> O operand (TMEM, over the dead Q operand) ------------
-        mbar_wait(bar_mma, mma_phase);
-        mma_phase ^= 1;
+        mbar_wait(bar_grp, grp_phase);
+        grp_phase ^= 1;
         umma::fence_after_sync();
         {
           uint32_t orr[2][16];
 #pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) umma::ld16_nw(tl + TC_COL_O + 16 * (4 * kh + 2 * i2 + hh), orr[i2]);
+          for (int i2 = 0; i2 < 2; ++i2) umma::ld16_nw(tl + TC_COL_O + 16 * (4 * grp + 2 * kh + i2), orr[i2]);
           umma::wait_ld();
 #pragma unroll
           for (int i2 = 0; i2 < 2; ++i2) {
-            const int head = 4 * kh + 2 * i2 + hh;
+            const int head = 4 * grp + 2 * kh + i2;
             const float lsel = kh ? (i2 ? lt3 : lt2) : (i2 ? lt1 : lt0);
             const float inv_l = act ? 1.f / lsel : 0.f;
             uint32_t hw[8], lw[8];
 #pragma unroll
-            for (int d2 = 0; d2 < 8; ++d2) {
-              __half h0, l0, h1, l1;
-              umma::split_f16(act ? umma::after_wait(orr[i2][2 * d2]) * inv_l : 0.f, h0, l0);
-              umma::split_f16(act ? umma::after_wait(orr[i2][2 * d2 + 1]) * inv_l : 0.f, h1, l1);
-              hw[d2] = umma::pack_h2(h0, h1);
-              lw[d2] = umma::pack_h2(l0, l1);
-            }
+            for (int d2 = 0; d2 < 8; ++d2)
+              umma::split2_f16(act ? umma::after_wait(orr[i2][2 * d2]) * inv_l : 0.f,
+                               act ? umma::after_wait(orr[i2][2 * d2 + 1]) * inv_l : 0.f, hw[d2], lw[d2]);
             umma::st8(tl + TC_COL_Q + 8 * head, hw);
             umma::st8(tl + TC_COL_Q + 64 + 8 * head, lw);
           }
@@ -624,13 +612,13 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma::mma_f16_ts(d, tm + TC_COL_Q + 8 * ks, umma::make_desc(opE + ks * 2 * lboN, lboN, 128), idescS, true);
-          umma::commit(bar_mma);
+          umma::commit(bar_sc);
         }
         PHASE_MARK(3);
 
         // ---- B3: logits of this thread's node columns [wsub*CQ, wsub*CQ + CQ) -----------------------------------
-        mbar_wait(bar_mma, mma_phase);
-        mma_phase ^= 1;
+        mbar_wait(bar_sc, sc_phase);
+        sc_phase ^= 1;
         umma::fence_after_sync();
         {
           uint32_t xr[28];

@@ -136,6 +136,21 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// two values at once: packed conversions (F2FP.PACK_AB) instead of four scalar F2F, which throttle on the MIO queue
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);          // a -> low half (even k), b -> high half
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 2^x by the SFU alone (MUFU.EX2): -inf -> 0, results below 2^-126 flush to 0
+__device__ __forceinline__ float ex2_raw(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // byte offset of element (r, k) inside a K-major no-swizzle operand with `lbo` bytes between 8-column chunks
 __device__ __forceinline__ uint32_t elem_off(int r, int k, uint32_t lbo) {
   return (uint32_t)(k >> 3) * lbo + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
