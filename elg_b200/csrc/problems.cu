@@ -69,8 +69,12 @@ __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int 
   const int j0 = problem == ELG_CVRP ? 1 : 0;
   const float xi = p[2 * i], yi = p[2 * i + 1];
   for (int j = threadIdx.x; j < N1; j += blockDim.x) sd[j] = dist2(xi - p[2 * j], yi - p[2 * j + 1]);
-  uint8_t* row = nbr + ((size_t)b * N1 + i) * ELG_NBR_STRIDE;
+  uint8_t* row = nbr + ((size_t)b * N1 + i) * ELG_NBR_NODE_BYTES(N1);
   for (int e = threadIdx.x; e < ELG_NBR_STRIDE; e += blockDim.x) row[e] = 0;
+  // pair features of get_cur_feature (CVRP/CVRPEnv.py:291-318, TSP/TSPEnv.py:135-156) for cur = i: distance and
+  // polar angle to every node, so the decode step gathers them instead of recomputing sqrt / atan2 per neighbour
+  float2* feat = reinterpret_cast<float2*>(row + ELG_NBR_STRIDE);
+  for (int j = threadIdx.x; j < N1; j += blockDim.x) feat[j] = make_float2(sd[j], atan2f(p[2 * j + 1] - yi, p[2 * j] - xi));
   __syncthreads();
   for (int j = j0 + threadIdx.x; j < N1; j += blockDim.x) {
     float dj = sd[j];
@@ -260,7 +264,7 @@ size_t elg_e_bytes(const elg_model_desc* d, int B, int N1) {
 
 size_t elg_nbr_bytes(const elg_model_desc* d, int B, int N1) {
   if (check_desc(d) || B <= 0 || N1 <= 1) return 0;
-  if (rollout_is_resident(d, N1)) return (size_t)B * N1 * ELG_NBR_STRIDE;
+  if (rollout_is_resident(d, N1)) return (size_t)B * N1 * ELG_NBR_NODE_BYTES(N1);
   const int NL = N1 - (d->problem == ELG_CVRP ? 1 : 0);
   return (size_t)B * N1 * ELG_NBR16_STRIDE(NL) * sizeof(uint16_t);
 }

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           // neighbour walk: first k valid entries of the distance-presorted list of `cur`
           if (RESIDENT) {
             uint4 Lw = make_uint4(0, 0, 0, 0);
-            if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_STRIDE) + s8);
+            if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_NODE_BYTES(N1)) + s8);
             const int iters = (NL + 7) >> 3;
 #pragma unroll
             for (int it = 0; it < 16; ++it) {

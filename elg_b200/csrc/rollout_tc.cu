@@ -406,13 +406,14 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
               uint8_t* ids = reinterpret_cast<uint8_t*>(sm + L.ids) + (warp * 4 + rq) * KT_MAX;
               const int cur = sCur[myr];
               const float ldv = sLoad[myr];
-              const float xc = sXY[2 * cur], yc = sXY[2 * cur + 1];
               const int NL = N1 - DEP, kloc = A.k_local;
               const uint32_t* mrow = sMask + myr * 4;
+              const uint8_t* nrow = reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_NODE_BYTES(N1);
+              const float2* feat = reinterpret_cast<const float2*>(nrow + ELG_NBR_STRIDE);      // (distance, angle) from cur
               int cnt = 0;
               {
                 uint4 Lw = make_uint4(0, 0, 0, 0);
-                if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_STRIDE) + s8);
+                if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(nrow) + s8);
                 const int iters = (NL + 7) >> 3;
 #pragma unroll
                 for (int it = 0; it < 16; ++it) {
@@ -432,31 +433,41 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
               const int kk = min(cnt, kloc);
               const int np = rlive ? kk + DEP : 0;
               __syncwarp();
-              float dmax = 0.f;
-              if (kk > 0) {
-                const int nl = ids[kk - 1];
-                dmax = dist2(xc - sXY[2 * nl], yc - sXY[2 * nl + 1]);
+              // features of this lane's entries: gathered from the per-instance pair table (same dist2 / atan2f values the
+              // kernel used to recompute); the three divisions become one reciprocal each per row
+              float2 ft[MAXE];
+#pragma unroll
+              for (int e = 0; e < MAXE; ++e) {
+                const int p = s8 + 8 * e;
+                node[e] = 0;
+                ft[e] = make_float2(0.f, 0.f);
+                if (p < np && !(DEP && p == 0)) {
+                  node[e] = ids[p - DEP];
+                  ft[e] = __ldg(feat + node[e]);
+                }
               }
+              float dmax = 0.f;
+              if (kk > 0) dmax = __ldg(feat + ids[kk - 1]).x;
+              const float r0d = dmax != 0.f ? 1.f / (dmax + 1e-6f) : 1.f;      // cvrp: cur_dist / (max + 1e-6); dmax == 0 -> dd itself
+              const float r1d = dmax != 0.f ? 1.f / dmax : 1.f;                 // penalty -d / dmax (no eps, CVRP/models.py:380,403)
+              const float rtsp = 1.f / (dmax + 1e-6f);
+              const float rld = 1.f / ldv;
               float f0[MAXE], f1[MAXE], f2[MAXE];
 #pragma unroll
               for (int e = 0; e < MAXE; ++e) {
                 const int p = s8 + 8 * e;
                 f0[e] = f1[e] = f2[e] = addv[e] = 0.f;
-                node[e] = 0;
                 if (p < np && !(DEP && p == 0)) {
-                  const int nd = ids[p - DEP];
-                  node[e] = nd;
-                  const float xn = sXY[2 * nd], yn = sXY[2 * nd + 1];
-                  const float dd = dist2(xc - xn, yc - yn);
+                  const float dd = ft[e].x;
                   if (CVRP) {
-                    f0[e] = dmax != 0.f ? dd / (dmax + 1e-6f) : dd;
-                    addv[e] = dmax != 0.f ? -(dd / dmax) : -dd;      // distance penalty
-                    f2[e] = sDem[nd] / ldv;
+                    f0[e] = dd * r0d;
+                    addv[e] = -(dd * r1d);
+                    f2[e] = sDem[node[e]] * rld;
                   } else {
-                    f0[e] = dd / (dmax + 1e-6f);
+                    f0[e] = dd * rtsp;
                     addv[e] = -f0[e];
                   }
-                  f1[e] = atan2f(yn - yc, xn - xc);
+                  f1[e] = ft[e].y;
                 }
               }
               float mown[4] = {0.f, 0.f, 0.f, 0.f};
@@ -620,6 +631,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         mbar_wait(bar_sc, sc_phase);
         sc_phase ^= 1;
         umma::fence_after_sync();
+        PHASE_MARK(7);
         {
           uint32_t xr[28];
           const int c0n = wsub * CQ;
@@ -629,6 +641,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           umma::wait_ld();
           float best = -INFINITY;
           int bidx = 0x7fffffff;
+          bool need_all = false;
           if (act) {
             const uint4 n4 = *reinterpret_cast<const uint4*>(sNb + rc * 4);
             const uint32_t nbw[4] = {n4.x, n4.y, n4.z, n4.w};
@@ -641,20 +654,52 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             rbase += wd > 2 ? __popc(nbw[2]) : 0;
             const float* arow = sAdd + rc * K1 + rbase;
             float* lo = A.out_logits ? A.out_logits + ((size_t)b * A.M + row0 + row) * N1 : nullptr;
+            // pass 1: pre-activation x = score + eb + {penalty + local | xi}; -inf where masked; first maximum
+            float xmax = -INFINITY;
+            int xidx = 0x7fffffff;
+#pragma unroll
+            for (int c4 = 0; c4 < 7; ++c4)
+              if (c4 * 4 < CQ) {
+#pragma unroll
+                for (int i = c4 * 4; i < c4 * 4 + 4; ++i) {
+                  float x = -INFINITY;
+                  if ((vwin >> i) & 1u) {
+                    const bool isnb = (nwin >> i) & 1u;
+                    const float add = isnb ? arow[__popc(nwin & ((1u << i) - 1u))] : A.xi;
+                    x = (umma::after_wait(xr[i]) + sEb[c0n + i]) + add;
+                    if (x > xmax) { xmax = x; xidx = c0n + i; }
+                  }
+                  xr[i] = __float_as_uint(x);
+                }
+              }
+            // tanh is monotone, so the arg-max of clip*tanh(x) is the arg-max of x unless fp32 tanh maps a smaller x to
+            // the same (or, by a 1-2 ulp wobble, larger) logit.  |d tanh| >= 4 e^(-2|x|) |dx| near the maximum, so only
+            // pre-activations within w = max(1e-4, 5e-7 e^(2|xmax|)) of it can tie (w covers ~4 ulp of tanh); in the
+            // saturated range that is a wide window, otherwise just the maximum -> a single tanh per row.
+            const float thr = xmax - fmaxf(1e-4f, 5e-7f * __expf(2.f * fabsf(xmax)));
+            int ncand = 0;
+#pragma unroll
+            for (int c4 = 0; c4 < 7; ++c4)
+              if (c4 * 4 < CQ) {
+#pragma unroll
+                for (int i = c4 * 4; i < c4 * 4 + 4; ++i) ncand += (__uint_as_float(xr[i]) >= thr && __uint_as_float(xr[i]) != -INFINITY) ? 1 : 0;
+              }
+            need_all = ncand > 1 || lo != nullptr;
+            if (ncand == 1) { best = A.clip * tanhf(xmax); bidx = xidx; }
+          }
+          const bool slow = __any_sync(FULL, need_all);
+          if (slow) {        // rare (ties / saturation) or diagnostic (logits requested): every logit
+            float* lo = (act && A.out_logits) ? A.out_logits + ((size_t)b * A.M + row0 + row) * N1 : nullptr;
+            if (need_all) { best = -INFINITY; bidx = 0x7fffffff; }
 #pragma unroll
             for (int c4 = 0; c4 < 7; ++c4)
               if (c4 * 4 < CQ) {
 #pragma unroll
                 for (int i = c4 * 4; i < c4 * 4 + 4; ++i) {
                   const int j = c0n + i;
-                  float v = -INFINITY;
-                  if ((vwin >> i) & 1u) {
-                    const float x = umma::after_wait(xr[i]) + sEb[j];
-                    const bool isnb = (nwin >> i) & 1u;
-                    const float add = isnb ? arow[__popc(nwin & ((1u << i) - 1u))] : A.xi;
-                    v = A.clip * tanhf(x + add);
-                    if (v > best) { best = v; bidx = j; }
-                  }
+                  const float x = __uint_as_float(xr[i]);
+                  const float v = (need_all && x != -INFINITY) ? A.clip * tanhf(x) : -INFINITY;
+                  if (need_all && v > best) { best = v; bidx = j; }
                   if (lo && j < N1) lo[j] = v;
                 }
               }

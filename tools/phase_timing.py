@@ -21,7 +21,7 @@ from elg_b200.cvrp.test import solve_batch
 from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
 
 TC = os.environ.get("ELG_B200_ATTENTION") == "tensor"
-NAMES = (["Q build", "softmax+P (4 rounds)", "B1 (2 passes)", "O operand", "B3", "select+C", "end barrier", "-"] if TC else
+NAMES = (["Q build", "softmax+P (4 rounds)", "B1 (2 passes)", "O operand", "B3", "select+C", "end barrier", "score MMA wait"] if TC else
          ["A", "A-barrier", "B1", "copy", "copy-barrier", "B3+C", "end-barrier", "-"])
 dev = "cuda:0"
 fn = _lib.lib.elg_debug_phase_clocks_tc if TC else _lib.lib.elg_debug_phase_clocks
