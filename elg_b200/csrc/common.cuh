@@ -35,7 +35,13 @@ constexpr int LOC_WCT = LOC_PE + KT_MAX * LE; // [LE][LE]     WCT[c][c'] = Wo_l[
 constexpr int LOC_BC = LOC_WCT + LE * LE;     // [LE]
 constexpr int LOC_WE = LOC_BC + LE;           // [LE][4]      We[c][f]
 constexpr int LOC_BE = LOC_WE + LE * 4;       // [LE]
-constexpr int LOC_TOTAL = LOC_BE + LE;
+// everything downstream of the local attention output ol is linear in it; folded for rollout_tc.cu (x 1/sqrt(LE)):
+//   local score of entry p = f_p . z + z3 + PW[p] . ol + PB[p],   z = ZW^T ol + ZB
+constexpr int LOC_PW = LOC_BE + LE;           // [KT_MAX][LE] sum_c' PE(p)[c'] Wo_l[c'][c] / sqrt(LE)
+constexpr int LOC_PB = LOC_PW + KT_MAX * LE;  // [KT_MAX]     PE(p) . bo_l / sqrt(LE)
+constexpr int LOC_ZW = LOC_PB + KT_MAX;       // [LE][4]      f < 3: sum_c' We[c'][f] Wo_l[c'][c];  f = 3: sum_c' be[c'] Wo_l[c'][c]   (/ sqrt(LE))
+constexpr int LOC_ZB = LOC_ZW + LE * 4;       // [4]          We^T bo_l, be . bo_l                                                    (/ sqrt(LE))
+constexpr int LOC_TOTAL = LOC_ZB + 4;
 constexpr int DER_FOLD_TOTAL = DER_LOC + LOC_TOTAL;
 // After the folds: every GEMM weight matrix pre-split into fp16 hi/lo tcgen05 B-operand tiles (one float's worth
 // of bytes per weight element).  Matrix W[N][K] -> tiles (n/128, k/64), each [hi 16 KB | lo 16 KB] in the K-major

@@ -125,6 +125,30 @@ __global__ void prepare_kernel(elg_model_desc d, elg_weight_layout_t L, const fl
     int c = i / LE, c2 = i % LE;                 // WCT[c][c2] = Wo_l[c2][c]
     loc[LOC_WCT + i] = w[L.loc_wo + c2 * LE + c];
   }
+  // folds of everything downstream of ol (mh = Wo_l ol + bo_l; z = We^T mh; c0 = be . mh; pem_p = PE(p) . mh), x 1/sqrt(LE)
+  const double isl = 1.0 / sqrt((double)LE);
+  for (int i = tid; i < KT_MAX * LE; i += nt) {
+    int p = i / LE, c = i % LE;
+    double a = 0;
+    for (int k = 0; k < LE; ++k) a += (double)pe[p][k] * (double)w[L.loc_wo + k * LE + c];
+    loc[LOC_PW + i] = (float)(a * isl);
+  }
+  for (int p = tid; p < KT_MAX; p += nt) {
+    double a = 0;
+    for (int k = 0; k < LE; ++k) a += (double)pe[p][k] * (double)w[L.loc_bo + k];
+    loc[LOC_PB + p] = (float)(a * isl);
+  }
+  for (int i = tid; i < LE * 4; i += nt) {
+    int c = i / 4, f = i % 4;
+    double a = 0;
+    for (int k = 0; k < LE; ++k) a += (f < 3 ? (double)we[k][f] : (double)w[L.loc_be + k]) * (double)w[L.loc_wo + k * LE + c];
+    loc[LOC_ZW + i] = (float)(a * isl);
+  }
+  for (int f = tid; f < 4; f += nt) {
+    double a = 0;
+    for (int k = 0; k < LE; ++k) a += (f < 3 ? (double)we[k][f] : (double)w[L.loc_be + k]) * (double)w[L.loc_bo + k];
+    loc[LOC_ZB + f] = (float)(a * isl);
+  }
 }
 
 // W[N][K] (fp32, leading dimension ld) -> fp16 hi/lo B-operand tiles for tc_gemm_kernel
