@@ -328,9 +328,14 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           umma::fence_after_sync();
           const uint32_t sb = tl + TC_COL_S + grp * N1p;
           uint32_t sr[56];
-#pragma unroll
-          for (int c8 = 0; c8 < 7; ++c8)
-            if (c8 * 8 < KH) umma::ld8_nw(sb + kh * KH + c8 * 8, sr + c8 * 8);
+          // KH = 8..56 columns in at most three loads (32 + 16 + 8, register i <-> column i); columns past KH that the
+          // fixed shapes drag along lie inside the allocation and are never used
+          {
+            const uint32_t s0 = sb + kh * KH;
+            umma::ld32_nw(s0, sr);
+            if (KH > 32) umma::ld16_nw(s0 + 32, sr + 32);
+            if (KH > 48) umma::ld8_nw(s0 + 48, sr + 48);
+          }
           umma::wait_ld();
           float mloc = -INFINITY;
 #pragma unroll
@@ -656,9 +661,12 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         {
           uint32_t xr[28];
           const int c0n = wsub * CQ;
-#pragma unroll
-          for (int c4 = 0; c4 < 7; ++c4)
-            if (c4 * 4 < CQ) umma::ld4_nw(tl + TC_COL_S + c0n + c4 * 4, xr + c4 * 4);
+          {
+            const uint32_t s0 = tl + TC_COL_S + c0n;
+            umma::ld16_nw(s0, xr);
+            if (CQ > 16) umma::ld8_nw(s0 + 16, xr + 16);
+            if (CQ > 24) umma::ld4_nw(s0 + 24, xr + 24);
+          }
           umma::wait_ld();
           float best = -INFINITY;
           int bidx = 0x7fffffff;
