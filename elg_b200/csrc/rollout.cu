@@ -1007,7 +1007,9 @@ static bool use_tensor_attention(const elg_model_desc* d, const RolloutArgs& a) 
   const int tiles = rollout_tc_tiles(d, a.B, a.M, a.N1, nullptr);
   if (tiles <= 0) return false;
   if (d->flags & ELG_FLAG_ATTN_TENSOR) return true;
-  return false;      // automatic choice: the fp32-pipe kernel until the tensor-core kernel is the faster one
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return a.B * tiles >= sms;      // few aug-instances (library runs, B = 8): small row tiles of the fp32-pipe kernel fill the machine better
 }
 
 static int launch_rollout(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) {

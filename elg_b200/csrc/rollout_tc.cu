@@ -253,21 +253,20 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           }
         }
         // ---- Q operand: q = Wq_last [enc[cur]; load] (cvrp) / q_first + Wq_last enc[cur] (tsp), fp16 hi/lo -> TMEM ----
-#pragma unroll
-        for (int i2 = 0; i2 < 2; ++i2) {
-          const int head = 2 * wsub + i2;
-          uint32_t hw[8], lw[8];
+        {
+          uint32_t hw[16], lw[16];                     // heads 2*wsub, 2*wsub + 1: 32 consecutive k
           if (act) {
-            const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur0) * E + head * D);
+            const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur0) * E + 2 * wsub * D);
+            const float4* fp = CVRP ? nullptr : reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + sFirst[rc]) * E + 2 * wsub * D);
 #pragma unroll
-            for (int d4 = 0; d4 < D / 4; ++d4) {
+            for (int d4 = 0; d4 < 2 * D / 4; ++d4) {
               float4 v4 = __ldg(qp + d4);
               if (CVRP) {
-                const float4 wl = *reinterpret_cast<const float4*>(sWL + head * D + d4 * 4);
+                const float4 wl = *reinterpret_cast<const float4*>(sWL + 2 * wsub * D + d4 * 4);
                 v4.x = fmaf(ld0, wl.x, v4.x); v4.y = fmaf(ld0, wl.y, v4.y);
                 v4.z = fmaf(ld0, wl.z, v4.z); v4.w = fmaf(ld0, wl.w, v4.w);
               } else {
-                const float4 f4 = __ldg(reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + sFirst[rc]) * E + head * D) + d4);
+                const float4 f4 = __ldg(fp + d4);
                 v4.x = f4.x + v4.x; v4.y = f4.y + v4.y; v4.z = f4.z + v4.z; v4.w = f4.w + v4.w;
               }
               umma::split2_f16(v4.x, v4.y, hw[d4 * 2], lw[d4 * 2]);
@@ -275,10 +274,10 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) hw[i] = lw[i] = 0u;
+            for (int i = 0; i < 16; ++i) hw[i] = lw[i] = 0u;
           }
-          umma::st8(tl + TC_COL_Q + 8 * head, hw);
-          umma::st8(tl + TC_COL_Q + 64 + 8 * head, lw);
+          umma::st16s<1>(tl + TC_COL_Q + 16 * wsub, hw);
+          umma::st16s<1>(tl + TC_COL_Q + 64 + 16 * wsub, lw);
         }
         umma::wait_st();
         umma::fence_before_sync();
@@ -376,13 +375,16 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
 #pragma unroll
           for (int c8 = 0; c8 < 7; ++c8)
             if (c8 * 8 < KH) {
-              uint32_t hw[4], lw[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                umma::split2_f16(__uint_as_float(sr[c8 * 8 + 2 * i]) * cown, __uint_as_float(sr[c8 * 8 + 2 * i + 1]) * cown, hw[i], lw[i]);
-              umma::st4(sb + kh * (KH >> 1) + c8 * 4, hw);
-              umma::st4(sb + (N1p >> 1) + kh * (KH >> 1) + c8 * 4, lw);
+              for (int i = c8 * 4; i < c8 * 4 + 4; ++i) {       // keys (2i, 2i+1) -> hi word in sr[2i], lo word in sr[2i+1]
+                uint32_t hwd, lwd;
+                umma::split2_f16(__uint_as_float(sr[2 * i]) * cown, __uint_as_float(sr[2 * i + 1]) * cown, hwd, lwd);
+                sr[2 * i] = hwd;
+                sr[2 * i + 1] = lwd;
+              }
             }
+          umma::st_words<2>(sb + kh * (KH >> 1), sr, KH >> 1);
+          umma::st_words<2>(sb + (N1p >> 1) + kh * (KH >> 1), sr + 1, KH >> 1);
           umma::wait_st();
           umma::fence_before_sync();
           group_sync(9 + grp);
@@ -615,23 +617,20 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         grp_phase ^= 1;
         umma::fence_after_sync();
         {
-          uint32_t orr[2][16];
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) umma::ld16_nw(tl + TC_COL_O + 16 * (4 * grp + 2 * kh + i2), orr[i2]);
+          uint32_t orr[32], hw[16], lw[16];            // heads 4*grp + 2*kh, + 1: 32 consecutive accumulator columns
+          umma::ld32_nw(tl + TC_COL_O + 16 * (4 * grp + 2 * kh), orr);
           umma::wait_ld();
 #pragma unroll
           for (int i2 = 0; i2 < 2; ++i2) {
-            const int head = 4 * grp + 2 * kh + i2;
             const float lsel = kh ? (i2 ? lt3 : lt2) : (i2 ? lt1 : lt0);
             const float inv_l = act ? 1.f / lsel : 0.f;
-            uint32_t hw[8], lw[8];
 #pragma unroll
             for (int d2 = 0; d2 < 8; ++d2)
-              umma::split2_f16(act ? umma::after_wait(orr[i2][2 * d2]) * inv_l : 0.f,
-                               act ? umma::after_wait(orr[i2][2 * d2 + 1]) * inv_l : 0.f, hw[d2], lw[d2]);
-            umma::st8(tl + TC_COL_Q + 8 * head, hw);
-            umma::st8(tl + TC_COL_Q + 64 + 8 * head, lw);
+              umma::split2_f16(act ? umma::after_wait(orr[i2 * 16 + 2 * d2]) * inv_l : 0.f,
+                               act ? umma::after_wait(orr[i2 * 16 + 2 * d2 + 1]) * inv_l : 0.f, hw[i2 * 8 + d2], lw[i2 * 8 + d2]);
           }
+          umma::st16s<1>(tl + TC_COL_Q + 8 * (4 * grp + 2 * kh), hw);
+          umma::st16s<1>(tl + TC_COL_Q + 64 + 8 * (4 * grp + 2 * kh), lw);
           umma::wait_st();
           umma::fence_before_sync();
         }

@@ -71,6 +71,42 @@ __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void st4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
+// strided register lists (r[0], r[S], r[2S], ...): lets hi / lo words interleaved in one array go out as wide stores
+template <int S>
+__device__ __forceinline__ void st4s(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[S]), "r"(r[2 * S]), "r"(r[3 * S]) : "memory");
+}
+template <int S>
+__device__ __forceinline__ void st8s(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[S]),
+               "r"(r[2 * S]), "r"(r[3 * S]), "r"(r[4 * S]), "r"(r[5 * S]), "r"(r[6 * S]), "r"(r[7 * S]) : "memory");
+}
+template <int S>
+__device__ __forceinline__ void st16s(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[S]), "r"(r[2 * S]), "r"(r[3 * S]), "r"(r[4 * S]), "r"(r[5 * S]), "r"(r[6 * S]), "r"(r[7 * S]),
+      "r"(r[8 * S]), "r"(r[9 * S]), "r"(r[10 * S]), "r"(r[11 * S]), "r"(r[12 * S]), "r"(r[13 * S]), "r"(r[14 * S]), "r"(r[15 * S])
+      : "memory");
+}
+// n = 4, 8, ..., 28 words (stride S registers apart) to consecutive columns in at most three stores
+template <int S>
+__device__ __forceinline__ void st_words(uint32_t taddr, const uint32_t* r, int n) {
+  if (n >= 16) {
+    st16s<S>(taddr, r);
+    if (n >= 24) {
+      st8s<S>(taddr + 16, r + 16 * S);
+      if (n >= 28) st4s<S>(taddr + 24, r + 24 * S);
+    } else if (n >= 20) {
+      st4s<S>(taddr + 16, r + 16 * S);
+    }
+  } else if (n >= 8) {
+    st8s<S>(taddr, r);
+    if (n >= 12) st4s<S>(taddr + 8, r + 8 * S);
+  } else {
+    st4s<S>(taddr, r);
+  }
+}
 __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
