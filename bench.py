@@ -34,8 +34,9 @@ WEIGHT_SEED, INSTANCE_SEED = 1234, 1234
 ALG_BYTES_PER_AUG_STEP = 161548        # K+V+enc re-read + node statics + row state, CVRP100
 ALG_FLOP_PER_ROW_STEP = 329088         # reference arithmetic per decode row-step, CVRP100
 # dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the ncu --set full capture
-# (profiles/r01_rollout_v3_ncu.md: 124.4 MB for a 480-aug-instance launch): the decoder tables are read once per rollout
-NCU_DRAM_BYTES_PER_AUG_INSTANCE = 124.4e6 / 480
+# (profiles/r01_rollout_tc_ncu.md: 875.8 MB for a 2400-aug-instance launch): the tensor-core operands are read once per
+# rollout, the per-step gathers (query rows, pair features) mostly hit L2
+NCU_DRAM_BYTES_PER_AUG_INSTANCE = 875.8e6 / 2400
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
@@ -260,18 +261,19 @@ def run_ours(args):
                     "d2h_bytes_per_step": 2 * nb * 4 + AUG * nb * POMO * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
-            "roofline": {"kernel": "rollout_kernel<CVRP> (decode step + env step, whole rollout in one launch)",
+            "roofline": {"kernel": "rollout_tc_kernel<CVRP> (decode step + env step, whole rollout in one launch)",
                          "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src,
                          "traffic": NCU_DRAM_BYTES_PER_AUG_INSTANCE * nb * AUG,
-                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_rollout_v3_ncu.md",
+                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_rollout_tc_ncu.md",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_AUG_STEP * aug_steps / max(len(events), 1),
                          "algorithmic_bytes_per_aug_instance_step": ALG_BYTES_PER_AUG_STEP,
                          "aug_instance_steps_per_launch": aug_steps / max(len(events), 1),
                          "kernel_ms_per_launch": k_ms / max(len(events), 1),
                          "kernel_share_of_step": k_ms / ms_dev,
-                         "note": "K/V/E' stay resident in shared memory for the whole rollout, so the streaming-model "
-                                 "HBM bytes are (by design) not moved; the binding unit is the fp32 FMA pipe, see fp32"},
+                         "note": "K'/V/E' stay resident in shared memory for the whole rollout, so the streaming-model "
+                                 "HBM bytes are (by design) not moved; the kernel is issue/latency-bound (ncu: ~50% issue "
+                                 "slots, tensor pipe 5%), see fp32 for the throughput-equivalent"},
             "fp32": {"achieved": ach_tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FP32_PEAK_TFLOPS,
                      "flop_per_row_step": ALG_FLOP_PER_ROW_STEP,
                      "note": "reference-arithmetic FLOPs (SURVEY 8d) / rollout-kernel time; peak = 148 SM x 128 FMA x 2 x 1.965 GHz"},

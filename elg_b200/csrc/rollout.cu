@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
         A.reward[g] = -len;
         if (A.logp) A.logp[g] = sLogp[r];
       }
-      if (tid == 0) A.n_steps[work] = t;
+      if (tid == 0) A.n_steps[b * A.ns_stride + tile] = t;
     }
     __syncthreads();
   }
@@ -1065,7 +1065,7 @@ int elg_rollout_tiles(const elg_model_desc* d, int B, int M, int N1) {
   if (check_desc(d) || M <= 0 || B <= 0) return -1;
   Plan p;
   if (make_plan(d, B, M, N1, p)) return -1;
-  const int tc = rollout_tc_tiles(d, B, M, N1, nullptr);      // the tensor-core kernel never uses more tiles
+  const int tc = rollout_tc_tiles(d, B, M, N1, nullptr);      // whichever kernel runs, n_steps is strided by this value
   return p.tiles > tc ? p.tiles : tc;
 }
 
@@ -1100,6 +1100,7 @@ int elg_rollout(const elg_model_desc* d, const float* derived, const elg_tables*
   ELG_REQUIRE(t_max >= need, ELG_EINVAL, "t_max=%d too small, need >= %d", t_max, need);
   a.start_nodes = start_nodes; a.mode = mode; a.seed = seed; a.t_max = t_max;
   a.tours = tours; a.reward = reward; a.n_steps = n_steps; a.logp = logp; a.work_counter = work_counter;
+  a.ns_stride = elg_rollout_tiles(d, B, M, N1);
   return launch_rollout(d, a, (cudaStream_t)stream);
 }
 

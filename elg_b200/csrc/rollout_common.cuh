@@ -22,6 +22,7 @@ struct RolloutArgs {
   elg_tables t;
   const float* derived;
   int problem, B, M, N1, MT, tiles, k_local;
+  int ns_stride;      // n_steps is indexed [aug-instance * ns_stride + tile] (ns_stride = elg_rollout_tiles())
   float xi, clip;
   const int32_t* start_nodes;
   int mode;

@@ -851,7 +851,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         A.reward[g] = -len;
         if (A.logp) A.logp[g] = sLogp[r];
       }
-      if (tid == 0) A.n_steps[work] = t;
+      if (tid == 0) A.n_steps[b * A.ns_stride + tile] = t;
     }
     __syncthreads();
   }

@@ -162,7 +162,8 @@ int elg_encode(const elg_model_desc* desc, const float* weights, const float* de
  *   start_nodes [M]      POMO start permutation (python random.sample on the host)
  *   tours [B][M][t_max]  int16, must be zero-filled by the caller; t_max >= 2*N1+2 (cvrp) / N1 (tsp)
  *   reward [B][M]        minus tour length (rounded unscaled length if t->unscaled != NULL)
- *   n_steps [B*tiles]    steps each CTA ran; the batch length T is their maximum
+ *   n_steps [B*tiles]    zero-initialised by the caller; entry [b*tiles + tile] = steps that row tile ran (tiles =
+ *                        elg_rollout_tiles(); unused entries stay 0); the batch length T is the maximum
  *   logp [B][M]          sample mode: sum of log-probabilities of the sampled actions (may be NULL)
  *   work_counter         one zero-initialised int32 (dynamic CTA scheduler)
  * elg_rollout_tiles() returns the number of row tiles per aug-instance used for (B, M, N1);
