@@ -31,7 +31,7 @@ namespace elg {
 
 // ---- shared-memory layout (offsets in floats) ---------------------------------------------------
 struct SmemLayout {
-  int k, v, e, o, eb, xy, dem, wl, u, tt, a, cv, vpe, pe, wct, bc, we, be;
+  int k, v, e, o, eb, xy, dem, wl, u, tt, a, vpe, pw, pb, zw, zb;
   int cur, first, load, tlen, fin, logp, mask, vis, ids, dense, ctrl, bar;
   int total;     // floats
 };
@@ -52,14 +52,12 @@ __host__ __device__ inline SmemLayout make_layout(int N1, int MT, int KT, bool r
   L.wl = o; o += E;
   L.u = o; o += LH * 4;
   L.tt = o; o += LH * KT_MAX;
-  L.a = o; o += LE * 4;
-  L.cv = o; o += LE;
+  L.a = o; o += LE * 4;                     // (Wv We)[c][0..2], (Wv be)[c]
   L.vpe = o; o += KT * TS;
-  L.pe = o; o += KT * TS;
-  L.wct = o; o += LE * LE;
-  L.bc = o; o += LE;
-  L.we = o; o += LE * 4;
-  L.be = o; o += LE;
+  L.pw = o; o += KT * TS;
+  L.pb = o; o += KT_MAX;
+  L.zw = o; o += LE * 4;
+  L.zb = o; o += 4;
   L.cur = o; o += MT;
   L.first = o; o += MT;
   L.load = o; o += MT;
@@ -91,13 +89,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
   const float* sU = sm + L.u;
   const float* sT = sm + L.tt;
   const float* sA = sm + L.a;
-  const float* sCV = sm + L.cv;
   const float* sVPE = sm + L.vpe;
-  const float* sPE = sm + L.pe;
-  const float* sWCT = sm + L.wct;
-  const float* sBC = sm + L.bc;
-  const float* sWE = sm + L.we;
-  const float* sBE = sm + L.be;
+  const float* sPW = sm + L.pw;
+  const float* sPB = sm + L.pb;
+  const float* sZW = sm + L.zw;
+  const float* sZB = sm + L.zb;
   int* sCur = reinterpret_cast<int*>(sm + L.cur);
   int* sFirst = reinterpret_cast<int*>(sm + L.first);
   float* sLoad = sm + L.load;
@@ -121,14 +117,17 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
     for (int i = tid; i < E; i += RT) w[L.wl + i] = A.derived[DER_WL + i];
     for (int i = tid; i < LH * 4; i += RT) w[L.u + i] = loc[LOC_U + i];
     for (int i = tid; i < LH * KT_MAX; i += RT) w[L.tt + i] = loc[LOC_T + i];
-    for (int i = tid; i < LE * 4; i += RT) { w[L.a + i] = loc[LOC_A + i]; w[L.we + i] = loc[LOC_WE + i]; }
-    for (int i = tid; i < LE; i += RT) { w[L.cv + i] = loc[LOC_CV + i]; w[L.bc + i] = loc[LOC_BC + i]; w[L.be + i] = loc[LOC_BE + i]; }
+    for (int i = tid; i < LE * 4; i += RT) {
+      w[L.a + i] = (i & 3) == 3 ? loc[LOC_CV + (i >> 2)] : loc[LOC_A + i];
+      w[L.zw + i] = loc[LOC_ZW + i];
+    }
+    for (int i = tid; i < KT_MAX; i += RT) w[L.pb + i] = loc[LOC_PB + i];
+    for (int i = tid; i < 4; i += RT) w[L.zb + i] = loc[LOC_ZB + i];
     for (int i = tid; i < KT * LE; i += RT) {
       int p = i / LE, c = i % LE;
       w[L.vpe + p * TS + c] = loc[LOC_VPE + i];
-      w[L.pe + p * TS + c] = loc[LOC_PE + i];
+      w[L.pw + p * TS + c] = loc[LOC_PW + i];
     }
-    for (int i = tid; i < LE * LE; i += RT) w[L.wct + i] = loc[LOC_WCT + i];
     if (RESIDENT && tid == 0) {
       mbar_init(bar, 1);
       mbar_init(bar_mma, 1);
@@ -146,7 +145,6 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 #ifdef ELG_PHASE_TIMING
   unsigned long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
-  const float sqrt_le = 5.656854249492381f;   // sqrt(32), used as a divisor like the reference
 
   for (int iter = 0;; ++iter) {
     // ---- fetch work: dynamic (atomic counter) for rollouts, static for single decode steps ------
@@ -463,11 +461,18 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
           const int kk = min(cnt, kloc);
           np = rlive ? kk + DEP : 0;
           __syncwarp();
+          // features of this lane's entries.  Resident instances gather (distance, angle) from the pair table that
+          // neighbour_kernel wrote next to the lists; streaming instances compute them here.
+          const float2* feat = reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(A.t.nbr) +
+                                                               ((size_t)b * N1 + cur) * ELG_NBR_NODE_BYTES(N1) + ELG_NBR_STRIDE);
           float dmax = 0.f;
           if (kk > 0) {
             const int nl = ids[kk - 1];
-            dmax = dist2(xc - pXY[2 * nl], yc - pXY[2 * nl + 1]);
+            dmax = RESIDENT ? __ldg(feat + nl).x : dist2(xc - pXY[2 * nl], yc - pXY[2 * nl + 1]);
           }
+          const float r0d = CVRP ? (dmax != 0.f ? 1.f / (dmax + 1e-6f) : 1.f) : 1.f / (dmax + 1e-6f);      // cur_dist / (max + 1e-6)
+          const float r1d = dmax != 0.f ? 1.f / dmax : 1.f;        // cvrp penalty -d / dmax (no eps, CVRP/models.py:380,403)
+          const float rld = 1.f / ldv;
           float f0[MAXE], f1[MAXE], f2[MAXE];
 #pragma unroll
           for (int e = 0; e < MAXE; ++e) {
@@ -477,21 +482,28 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             if (p < np && !(DEP && p == 0)) {
               const int nd = ids[p - DEP];
               node[e] = nd;
-              const float xn = pXY[2 * nd], yn = pXY[2 * nd + 1];
-              const float dd = dist2(xc - xn, yc - yn);
-              if (CVRP) {
-                f0[e] = dmax != 0.f ? dd / (dmax + 1e-6f) : dd;
-                addv[e] = dmax != 0.f ? -(dd / dmax) : -dd;      // distance penalty
-                f2[e] = pDem[nd] / ldv;
+              float dd, th;
+              if (RESIDENT) {
+                const float2 ft = __ldg(feat + nd);
+                dd = ft.x; th = ft.y;
               } else {
-                f0[e] = dd / (dmax + 1e-6f);
+                const float xn = pXY[2 * nd], yn = pXY[2 * nd + 1];
+                dd = dist2(xc - xn, yc - yn);
+                th = atan2f(yn - yc, xn - xc);
+              }
+              f0[e] = dd * r0d;
+              f1[e] = th;
+              if (CVRP) {
+                addv[e] = -(dd * r1d);                             // distance penalty
+                f2[e] = pDem[nd] * rld;
+              } else {
                 addv[e] = -f0[e];
               }
-              f1[e] = atan2f(yn - yc, xn - xc);
             }
           }
-          // 4-head attention of the constant query over the local sequence
-          float mown[4] = {0.f, 0.f, 0.f, 0.f};       // this lane's 4 rows of mh = Wo_l ol + bo_l
+          // 4-head attention of the constant query over the local sequence.  Per head the octet reduces
+          // (sum, g0..2) to every lane and the 8 value columns reduce-scatter, so lane d ends up owning ol[h*8 + d].
+          float olh[LH];
 #pragma unroll
           for (int h = 0; h < LH; ++h) {
             const float u0 = sU[h * 4], u1 = sU[h * 4 + 1], u2 = sU[h * 4 + 2];
@@ -509,6 +521,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
               mx = fmaxf(mx, v);
             }
             mx = octet_max(mx);
+            const float mref = mx == -INFINITY ? 0.f : mx;
             float g0 = 0.f, g1 = 0.f, g2 = 0.f, sum = 0.f;
             float vp8[LD];
 #pragma unroll
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
 #pragma unroll
             for (int e = 0; e < MAXE; ++e) {
               const int p = s8 + 8 * e;
-              const float w = (p < np && sc[e] != -INFINITY) ? exp2f(sc[e] - mx) : 0.f;
+              const float w = umma::ex2_raw(sc[e] - mref);          // -inf (masked / beyond np) -> 0
               sum += w;
               g0 = fmaf(w, f0[e], g0); g1 = fmaf(w, f1[e], g1); g2 = fmaf(w, f2[e], g2);
               if (p < np) {
@@ -529,48 +542,66 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
               }
             }
             sum = octet_sum(sum);
-            const float inv = sum > 0.f ? 1.f / sum : 0.f;
-            g0 = octet_sum(g0) * inv; g1 = octet_sum(g1) * inv; g2 = octet_sum(g2) * inv;
+            const float inv_s = sum > 0.f ? 1.f / sum : 0.f;
+            g0 = octet_sum(g0) * inv_s; g1 = octet_sum(g1) * inv_s; g2 = octet_sum(g2) * inv_s;
+            // reduce-scatter of vp8 over the octet: after three exchange steps lane s8 holds the total of vp8[s8]
+            float r4[4], r2[2];
+            {
+              const bool up = (s8 & 4) != 0;
 #pragma unroll
-            for (int d = 0; d < LD; ++d) {
-              const float vps = octet_sum(vp8[d]) * inv;
-              const int c = h * LD + d;
-              // ol[c] = (Wv We)[c] . g + (Wv be)[c] + sum_p w_p (Wv PE(p))[c]
-              const float ol = fmaf(sA[c * 4 + 2], g2, fmaf(sA[c * 4 + 1], g1, sA[c * 4] * g0)) + sCV[c] + vps;
-              const float4 wc = *reinterpret_cast<const float4*>(sWCT + c * LE + s8 * 4);
-              mown[0] = fmaf(wc.x, ol, mown[0]); mown[1] = fmaf(wc.y, ol, mown[1]);
-              mown[2] = fmaf(wc.z, ol, mown[2]); mown[3] = fmaf(wc.w, ol, mown[3]);
+              for (int i = 0; i < 4; ++i) {
+                const float send = up ? vp8[i] : vp8[i + 4];
+                const float keep = up ? vp8[i + 4] : vp8[i];
+                r4[i] = keep + __shfl_xor_sync(FULL, send, 4);
+              }
             }
+            {
+              const bool up = (s8 & 2) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = up ? r4[i] : r4[i + 2];
+                const float keep = up ? r4[i + 2] : r4[i];
+                r2[i] = keep + __shfl_xor_sync(FULL, send, 2);
+              }
+            }
+            const bool up1 = (s8 & 1) != 0;
+            const float vps = ((up1 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, up1 ? r2[0] : r2[1], 1)) * inv_s;
+            // ol[c] = (Wv We)[c] . g + (Wv be)[c] + sum_p w_p (Wv PE(p))[c],  c = h*8 + s8
+            const float4 a4 = *reinterpret_cast<const float4*>(sA + (h * LD + s8) * 4);
+            olh[h] = fmaf(a4.z, g2, fmaf(a4.y, g1, a4.x * g0)) + a4.w + vps;
           }
+          // z = ZW^T ol + ZB (3 feature weights + constant), partial over this lane's four ol, then octet sum
           float z0 = 0.f, z1 = 0.f, z2 = 0.f, c0 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = s8 * 4 + i;
-            mown[i] += sBC[c];
-            z0 = fmaf(sWE[c * 4], mown[i], z0); z1 = fmaf(sWE[c * 4 + 1], mown[i], z1);
-            z2 = fmaf(sWE[c * 4 + 2], mown[i], z2); c0 = fmaf(sBE[c], mown[i], c0);
+          for (int h = 0; h < LH; ++h) {
+            const float4 zw = *reinterpret_cast<const float4*>(sZW + (h * LD + s8) * 4);
+            z0 = fmaf(zw.x, olh[h], z0); z1 = fmaf(zw.y, olh[h], z1);
+            z2 = fmaf(zw.z, olh[h], z2); c0 = fmaf(zw.w, olh[h], c0);
           }
-          z0 = octet_sum(z0); z1 = octet_sum(z1); z2 = octet_sum(z2); c0 = octet_sum(c0);
-          // loc_p = (We f_p + be + PE(p)) . mh / sqrt(32)
+          z0 = octet_sum(z0) + sZB[0]; z1 = octet_sum(z1) + sZB[1]; z2 = octet_sum(z2) + sZB[2]; c0 = octet_sum(c0) + sZB[3];
+          // positional part PW[p] . ol of this lane's entries: ol broadcast four columns at a time
           float pem[MAXE];
 #pragma unroll
-          for (int e = 0; e < MAXE; ++e) pem[e] = 0.f;
+          for (int e = 0; e < MAXE; ++e) pem[e] = sPB[min(s8 + 8 * e, KT - 1)];
 #pragma unroll
-          for (int src = 0; src < 8; ++src) {
+          for (int h = 0; h < LH; ++h) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float mv = __shfl_sync(FULL, mown[i], (lane & 24) | src);
-              const int c = src * 4 + i;
+            for (int dq = 0; dq < 2; ++dq) {
+              const float o0 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 0));
+              const float o1 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 1));
+              const float o2 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 2));
+              const float o3 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 3));
 #pragma unroll
               for (int e = 0; e < MAXE; ++e) {
                 const int p = min(s8 + 8 * e, KT - 1);
-                pem[e] = fmaf(sPE[p * TS + c], mv, pem[e]);
+                const float4 pw = *reinterpret_cast<const float4*>(sPW + p * TS + h * LD + dq * 4);
+                pem[e] = fmaf(pw.w, o3, fmaf(pw.z, o2, fmaf(pw.y, o1, fmaf(pw.x, o0, pem[e]))));
               }
             }
           }
 #pragma unroll
-          for (int e = 0; e < MAXE; ++e)     // penalty + local score of this lane's entries
-            addv[e] += (fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e]) / sqrt_le;
+          for (int e = 0; e < MAXE; ++e)      // penalty + local score (tables carry the 1/sqrt(32))
+            addv[e] += fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e];
 
         }
       }
