@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _run(kind, N, M, n, aug, gain=3.0, seed=1):
+def _run(kind, N, M, n, aug, gain=3.0, seed=1, attention="fp32"):
     from elg_b200 import engine
     from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
     mp = dict(DEFAULT_MODEL_PARAMS[kind])
@@ -22,7 +22,7 @@ def _run(kind, N, M, n, aug, gain=3.0, seed=1):
         prob = O.load_tsp(synthetic_tsp_batch(n, N, seed=seed), aug)
     perm = O.start_permutation(kind, N, M, seed=seed)
     ref_t, _, ref_r = O.rollout(W, prob, M, perm, "greedy")
-    handle = engine.ModelHandle(kind, mp, sd, DEV)
+    handle = engine.ModelHandle(kind, mp, sd, DEV, attention=attention)
     batch = engine.encode(handle, prob.xy.to(DEV), None if prob.demand is None else prob.demand.to(DEV))
     tours16, reward, _, n_steps = engine.rollout(batch, M, perm.tolist())
     T = int(n_steps.max())
@@ -50,6 +50,52 @@ def test_ragged_shapes_match_oracle(kind, N, M, n, aug):
         O.check_feasible_cvrp(tours, prob.demand)
     else:
         assert torch.equal(tours.sort(dim=2)[0], torch.arange(N).expand_as(tours))
+
+
+@pytest.mark.parametrize("kind,N,M,n,aug", [
+    ("cvrp", 5, 1, 3, 1),       # N+1 = 6 -> one 16-column MMA tile, one live TMEM lane
+    ("cvrp", 7, 5, 2, 8),
+    ("cvrp", 15, 15, 2, 8),     # N+1 = 16: no padded key columns
+    ("cvrp", 45, 45, 1, 8),     # k = 40 < N; rows in two TMEM lane quadrants
+    ("cvrp", 70, 66, 1, 8),     # rows in three quadrants, M not a multiple of 4
+    ("cvrp", 111, 111, 1, 1),   # resident limit, 111 rows in one CTA
+    ("tsp", 4, 4, 2, 1),
+    ("tsp", 31, 31, 1, 8),
+    ("tsp", 100, 100, 1, 8),
+    ("tsp", 112, 112, 1, 1),    # 112 nodes, 112 rows: every TMEM column of the S buffers in use
+])
+def test_ragged_shapes_tensor_core_kernel(kind, N, M, n, aug):
+    tours, reward, ref_t, ref_r, prob = _run(kind, N, M, n, aug, attention="tensor")
+    frac, same = compare_tours(tours, ref_t)
+    assert frac >= 0.9, frac
+    assert ((reward - ref_r).abs() / ref_r.abs())[same].max() < 1e-4
+    if kind == "cvrp":
+        O.check_feasible_cvrp(tours, prob.demand)
+    else:
+        assert torch.equal(tours.sort(dim=2)[0], torch.arange(N).expand_as(tours))
+
+
+def test_automatic_kernel_choice_agrees_with_both():
+    """160 aug-instances >= 148 SMs -> the library picks the tensor-core kernel by itself; forcing either kernel gives the
+    same tours on (all but a handful of) rows and the same best costs."""
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
+    mp, sd = dict(DEFAULT_MODEL_PARAMS["cvrp"]), synthetic_state_dict("cvrp", seed=7, gain=3.0)
+    b = synthetic_cvrp_batch(20, 50, seed=3)
+    prob = O.load_cvrp(b["depot"], b["loc"], b["demand"], 8)
+    perm = O.start_permutation("cvrp", 50, 50, seed=3)
+    out = {}
+    for att in ("auto", "tensor", "fp32"):
+        h = engine.ModelHandle("cvrp", mp, sd, DEV, attention=att)
+        batch = engine.encode(h, prob.xy.to(DEV), prob.demand.to(DEV))
+        t16, rew, _, ns = engine.rollout(batch, 50, perm.tolist())
+        out[att] = (t16[:, :, :int(ns.max())].long().cpu(), rew.cpu())
+    assert torch.equal(out["auto"][0], out["tensor"][0]) and torch.equal(out["auto"][1], out["tensor"][1])
+    frac, same = compare_tours(out["tensor"][0], out["fp32"][0])
+    assert frac >= 0.97, frac
+    best_t, best_f = out["tensor"][1].max(1)[0], out["fp32"][1].max(1)[0]
+    assert ((best_t - best_f).abs() / best_f.abs()).max() < 2e-3
+    O.check_feasible_cvrp(out["tensor"][0], prob.demand)
 
 
 def test_out_of_envelope_fails_loudly():
