@@ -162,6 +162,154 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
 }
 
 
+// ---- encoder self-attention on tcgen05 (N1 <= 112): one CTA per (aug-instance, head) ----------------------------
+// S = Q K^T (SS form, M = 128 query rows, N = N1p keys, K = 16) -> TMEM; thread = query row: softmax in registers, P
+// (fp16 hi/lo, two keys per column) back into TMEM over S; O = P V (TS form, N = 16) -> TMEM columns [112, 128).
+// Split precision with the cross terms issued first (umma.cuh); q is pre-scaled by log2(e)/sqrt(D) (exp2 domain).
+__global__ void __launch_bounds__(128, 3) enc_attention_tc_kernel(const float* __restrict__ qkv, int N1,
+                                                                  float* __restrict__ att) {
+  __shared__ __align__(128) uint8_t sQ[2 * 4096];          // A operand hi | lo: 128 rows x 16 k
+  __shared__ __align__(128) uint8_t sK[2 * 112 * 32];      // B operand hi | lo: N1p keys x 16 k
+  __shared__ __align__(128) uint8_t sV[2 * 112 * 32];      // B operand hi | lo: 16 d x N1p keys
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int N1p = (N1 + 15) & ~15;
+  const int h = blockIdx.x % H;
+  const long long b = blockIdx.x / H;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r = tid;                                        // query row = key row = TMEM lane
+  const float* rowp = qkv + (b * N1 + r) * (3LL * E) + h * D;
+  const uint32_t khalf = (uint32_t)N1p * 32u;
+  {
+    uint32_t qh[8], ql[8], kh[8], kl[8];
+    float vv[D];
+    if (r < N1) {
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(rowp + d4 * 4);
+        const float4 k4 = *reinterpret_cast<const float4*>(rowp + E + d4 * 4);
+        const float4 v4 = *reinterpret_cast<const float4*>(rowp + 2 * E + d4 * 4);
+        const float sc = 0.36067376022224085f;              // log2(e) / sqrt(16)
+        umma::split2_f16(q4.x * sc, q4.y * sc, qh[d4 * 2], ql[d4 * 2]);
+        umma::split2_f16(q4.z * sc, q4.w * sc, qh[d4 * 2 + 1], ql[d4 * 2 + 1]);
+        umma::split2_f16(k4.x, k4.y, kh[d4 * 2], kl[d4 * 2]);
+        umma::split2_f16(k4.z, k4.w, kh[d4 * 2 + 1], kl[d4 * 2 + 1]);
+        vv[d4 * 4] = v4.x; vv[d4 * 4 + 1] = v4.y; vv[d4 * 4 + 2] = v4.z; vv[d4 * 4 + 3] = v4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qh[i] = ql[i] = kh[i] = kl[i] = 0u;
+#pragma unroll
+      for (int d = 0; d < D; ++d) vv[d] = 0.f;
+    }
+    const uint32_t ro = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    *reinterpret_cast<uint4*>(sQ + ro) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+    *reinterpret_cast<uint4*>(sQ + 2048 + ro) = make_uint4(qh[4], qh[5], qh[6], qh[7]);
+    *reinterpret_cast<uint4*>(sQ + 4096 + ro) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+    *reinterpret_cast<uint4*>(sQ + 4096 + 2048 + ro) = make_uint4(ql[4], ql[5], ql[6], ql[7]);
+    if (r < N1p) {
+      const uint32_t lbo = (uint32_t)N1p * 16u;
+      *reinterpret_cast<uint4*>(sK + ro) = make_uint4(kh[0], kh[1], kh[2], kh[3]);
+      *reinterpret_cast<uint4*>(sK + lbo + ro) = make_uint4(kh[4], kh[5], kh[6], kh[7]);
+      *reinterpret_cast<uint4*>(sK + khalf + ro) = make_uint4(kl[0], kl[1], kl[2], kl[3]);
+      *reinterpret_cast<uint4*>(sK + khalf + lbo + ro) = make_uint4(kl[4], kl[5], kl[6], kl[7]);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        __half hi, lo;
+        umma::split_f16(vv[d], hi, lo);
+        const uint32_t off = umma::elem_off(d, r, 256u);
+        *reinterpret_cast<__half*>(sV + off) = hi;
+        *reinterpret_cast<__half*>(sV + khalf + off) = lo;
+      }
+    }
+  }
+  umma::fence_async_smem();
+  if (warp == 0) umma::tmem_alloc(&tptr, 128);
+  if (tid == 0) umma::mbar_init(&bar, 1);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tm = tptr;
+  const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+  if (tid == 0) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N1p);
+    const uint32_t lbo = (uint32_t)N1p * 16u;
+    const uint64_t aHi = umma::make_desc(umma::smem_addr(sQ), 2048, 128), aLo = umma::make_desc(umma::smem_addr(sQ) + 4096, 2048, 128);
+    const uint64_t bHi = umma::make_desc(umma::smem_addr(sK), lbo, 128), bLo = umma::make_desc(umma::smem_addr(sK) + khalf, lbo, 128);
+    umma::mma_f16_ss(tm, aLo, bHi, idesc, false);
+    umma::mma_f16_ss(tm, aHi, bLo, idesc, true);
+    umma::mma_f16_ss(tm, aHi, bHi, idesc, true);
+    umma::commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::fence_after_sync();
+  uint32_t sr[112];
+  umma::ld32_nw(tl, sr);
+  if (N1p > 32) umma::ld32_nw(tl + 32, sr + 32);
+  if (N1p > 64) umma::ld32_nw(tl + 64, sr + 64);
+  if (N1p > 96) umma::ld16_nw(tl + 96, sr + 96);
+  umma::wait_ld();
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 7; ++c)
+    if (c * 16 < N1p) {
+#pragma unroll
+      for (int i = c * 16; i < c * 16 + 16; ++i) {
+        const float sv = i < N1 ? umma::after_wait(sr[i]) : -INFINITY;
+        sr[i] = __float_as_uint(sv);
+        mx = fmaxf(mx, sv);
+      }
+    }
+  const float moff = mx - 10.f;                             // weights 2^(s - max + 10): small ones stay out of fp16 subnormals
+  float l = 0.f;
+#pragma unroll
+  for (int c = 0; c < 7; ++c)
+    if (c * 16 < N1p) {
+#pragma unroll
+      for (int i = c * 8; i < c * 8 + 8; ++i) {
+        const float p0 = umma::ex2_raw(__uint_as_float(sr[2 * i]) - moff), p1 = umma::ex2_raw(__uint_as_float(sr[2 * i + 1]) - moff);
+        l += p0 + p1;
+        uint32_t hw, lw;
+        umma::split2_f16(p0, p1, hw, lw);
+        sr[2 * i] = hw;
+        sr[2 * i + 1] = lw;
+      }
+      umma::st8s<2>(tl + c * 8, sr + c * 16);                              // P hi: keys 16c .. 16c+15
+      umma::st8s<2>(tl + (N1p >> 1) + c * 8, sr + c * 16 + 1);             // P lo
+    }
+  umma::wait_st();
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    umma::fence_after_sync();
+    const uint32_t idesc = umma::make_idesc_f16(128, 16);
+    const uint32_t vHi = umma::smem_addr(sV), vLo = vHi + khalf, pHi = tm, pLo = tm + (N1p >> 1), dO = tm + 112;
+    const int nks = N1p >> 4;
+    for (int ks = 0; ks < nks; ++ks) umma::mma_f16_ts(dO, pLo + 8 * ks, umma::make_desc(vHi + ks * 512, 256, 128), idesc, ks > 0);
+    for (int ks = 0; ks < nks; ++ks) umma::mma_f16_ts(dO, pHi + 8 * ks, umma::make_desc(vLo + ks * 512, 256, 128), idesc, true);
+    for (int ks = 0; ks < nks; ++ks) umma::mma_f16_ts(dO, pHi + 8 * ks, umma::make_desc(vHi + ks * 512, 256, 128), idesc, true);
+    umma::commit(&bar);
+  }
+  umma::mbar_wait(&bar, 1);
+  umma::fence_after_sync();
+  {
+    uint32_t orr[16];
+    umma::ld16_nw(tl + 112, orr);
+    umma::wait_ld();
+    if (r < N1) {
+      const float inv = 1.f / l;
+      float* op = att + (b * N1 + r) * E + h * D;
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4)
+        *reinterpret_cast<float4*>(op + d4 * 4) = make_float4(umma::after_wait(orr[d4 * 4]) * inv, umma::after_wait(orr[d4 * 4 + 1]) * inv,
+                                                              umma::after_wait(orr[d4 * 4 + 2]) * inv, umma::after_wait(orr[d4 * 4 + 3]) * inv);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tm, 128);
+}
+
 // ---- decoder keys / values as fp16 hi/lo tcgen05 B operands (rollout_tc.cu), segments 1 and 2 of elg_tables.e ----
 //   K'  [N1p keys x 128 k]  element (j, c) at (c/8)*N1p*16 + (j/8)*128 + (j%8)*16 + (c%8)*2        (like E')
 //   V^T per head h: [16 d x N1p keys]  element (d, j) at h*N1p*32 + (j/8)*256 + (d/8)*128 + (d%8)*16 + (j%8)*2
@@ -505,7 +653,8 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
     float* xout = (l == d->layers - 1) ? t->enc : x;
     const long long so = split_off_layer(l, d->ff);
     ELG_TRY(tc_gemm<EPI_NONE>(x, derived, so, qkv, nullptr, nullptr, rows, 3 * E, E, 3 * E, st));
-    enc_attention_kernel<<<(unsigned)(B * H), 128, att_smem, st>>>(qkv, N1, att);
+    if (N1 <= 112) enc_attention_tc_kernel<<<(unsigned)(B * H), 128, 0, st>>>(qkv, N1, att);
+    else enc_attention_kernel<<<(unsigned)(B * H), 128, att_smem, st>>>(qkv, N1, att);
     ELG_LAUNCH_OK();
     ELG_TRY(tc_gemm<EPI_BIAS_RES>(att, derived, so + 3LL * E * E, tt, w + y.bo, x, rows, E, E, E, st));
     instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n1w, w + y.n1b, N1, x1);
