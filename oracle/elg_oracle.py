@@ -31,6 +31,9 @@ Reference map (file:line under /root/reference):
   tsp_env_step        TSP/TSPEnv.py:108-133
   tour_length         CVRP/CVRPEnv.py:251-288, TSP/TSPEnv.py:158-184
   rollout             CVRP/utils.py:7-29, TSP/utils.py:7-26
+  reinforce_loss      CVRP/train.py:112-121, TSP/train.py:107-119 (teacher-forced on recorded tours; torch
+                      autograd through this module is the gradient oracle of the training path)
+  adam_step           torch.optim.Adam(lr, weight_decay=1e-6) as constructed at CVRP/train.py:87
 """
 import math
 import random
@@ -128,6 +131,11 @@ class Weights:
 
     def __getitem__(self, k):
         return self.sd[k]
+
+    def requires_grad_(self, flag=True):
+        for v in self.sd.values():
+            v.requires_grad_(flag)
+        return self
 
 
 def _heads(t, h):
@@ -445,6 +453,71 @@ def rollout(W, prob, M, perm, mode="greedy", generator=None, cache=None, hook=No
         reward = -tour_length(prob.xy, tours)
     probs = None if mode == "greedy" else torch.stack(plist, dim=1)
     return tours, probs, reward
+
+
+# --------------------------------------------------------------------------- training objective
+
+def teacher_forced_logp(W, prob, M, tours, cache=None, hook=None):
+    """Sum over steps of log p(recorded action) per row, (B, M), differentiable w.r.t. the tensors in W.
+
+    Replays `tours` (B, M, T) through the environment; forced steps (cvrp: depot + POMO start, tsp: POMO start)
+    carry probability 1 (CVRP/CVRPModel.py:43-50, TSP/TSPModel.py:30-37), finished rows select the depot with
+    probability 1.  This is `probs.log().sum(dim=1)` of CVRP/train.py:115 for the same action sequence."""
+    if cache is None:
+        cache = decoder_cache(W, encode(W, prob))
+    B, _, T = tours.shape
+    logp = torch.zeros(B, M, dtype=prob.xy.dtype)
+    if W.kind == "cvrp":
+        st = cvrp_reset(prob, M)
+        for t in range(T):
+            sel = tours[:, :, t]
+            if t >= 2:
+                logits = decode_logits(W, prob, cache, st.cur, st.masked, st.load)
+                if hook is not None:
+                    hook(t, st, logits)
+                lp = torch.log_softmax(logits, dim=2).gather(2, sel[:, :, None]).squeeze(2)
+                logp = logp + torch.where(st.finished, torch.zeros_like(lp), lp)
+            cvrp_env_step(prob, st, sel)
+    else:
+        st = tsp_reset(prob, M)
+        for t in range(T):
+            sel = tours[:, :, t]
+            if t == 0:
+                set_first(W, cache, sel)
+            else:
+                logits = decode_logits(W, prob, cache, st.cur, st.masked.clone())   # the env updates its mask in place
+                if hook is not None:
+                    hook(t, st, logits)
+                logp = logp + torch.log_softmax(logits, dim=2).gather(2, sel[:, :, None]).squeeze(2)
+            tsp_env_step(prob, st, sel)
+    return logp
+
+
+def reinforce_coef(kind, reward, scale_norm=True):
+    """dJ/dlogp per row for J = mean(-(r - mean_m r) * logp [/ max_m(r - mean_m r)])  (CVRP/train.py:113-121;
+    TSP/train.py:114-117 skips the scaling unless every instance has a non-zero maximum advantage)."""
+    adv = reward - reward.mean(dim=1, keepdim=True)
+    coef = -adv
+    if scale_norm:
+        fac = adv.max(dim=1, keepdim=True)[0]
+        if kind == "cvrp" or bool((fac != 0).all()):
+            coef = coef / fac
+    return coef / reward.numel()
+
+
+def reinforce_loss(W, prob, M, tours, reward, scale_norm=True, hook=None):
+    """J of CVRP/train.py:112-121 for recorded tours and rewards (rewards carry no gradient)."""
+    logp = teacher_forced_logp(W, prob, M, tours, hook=hook)
+    return (reinforce_coef(W.kind, reward, scale_norm) * logp).sum(), logp
+
+
+def adam_step(p, g, m, v, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-6):
+    """One torch.optim.Adam update (L2 weight decay added to the gradient), step counted from 1."""
+    g = g + weight_decay * p
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    denom = v.sqrt() / math.sqrt(1 - beta2 ** step) + eps
+    return p - (lr / (1 - beta1 ** step)) * m / denom, m, v
 
 
 def best_of(reward, aug, n):
