@@ -85,13 +85,16 @@ def test_oracle_reinforce_gradient_matches_reference(name):
 def test_oracle_adam_step_matches_reference(name):
     g = TrainGolden(name)
     W, _, _, grads = oracle_grads(g)
+    rms = {k: float(g.z["g_norm/" + k]) / np.sqrt(grads[k].numel()) for k in g.meta["keys"]}
     for k in g.meta["keys"]:
+        if rms[k] < 1e-3 * max(rms.values()):
+            continue            # exact gradient is zero: Adam amplifies pure rounding noise to +-lr
         p = W.sd[k].detach()
         new_p, _, _ = O.adam_step(p, grads[k], torch.zeros_like(p), torch.zeros_like(p), 1, g.meta["lr"], weight_decay=g.meta["weight_decay"])
         idx = sample_idx(p.numel())
         ref = g.z["w_after/" + k]
         # the first Adam step moves every weight by ~lr * sign(g); entries whose gradient is ~0 are ill-conditioned
         gs = g.z["g_sample/" + k]
-        ok = np.abs(gs) > 1e-6 * max(np.abs(gs).max(), 1e-30)
+        ok = np.abs(gs) > 1e-3 * max(np.abs(gs).max(), 1e-30)
         diff = np.abs(new_p.reshape(-1).numpy()[idx] - ref)
         assert diff[ok].max(initial=0.0) < 2e-6, k
