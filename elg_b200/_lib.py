@@ -64,6 +64,14 @@ SYMBOLS = {
     "elg_env_step": (_I, [_I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "elg_cur_feature": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "elg_tour_length": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "elg_train_saved_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
+    "elg_encode_train": (_I, [C.POINTER(ModelDesc), _P, _P, C.POINTER(Tables), _I, _I, _P, _SZ, _P]),
+    "elg_train_workspace_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I, _I, _I, _I]),
+    "elg_train_workspace_layout": (_I, [C.POINTER(ModelDesc), _I, _I, _I, _I, C.POINTER(C.c_int64)]),
+    "elg_reinforce_backward": (_I, [C.POINTER(ModelDesc), _P, _P, C.POINTER(Tables), _P, _I, _I, _I, _P, _I, _I, _P, _P,
+                                    _I, _P, _P, _P, _SZ, _P]),
+    "elg_adam_step": (_I, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                           C.c_float, _P]),
     "elg_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

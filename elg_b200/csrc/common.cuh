@@ -52,6 +52,18 @@ __host__ __device__ inline long long split_off_layer(int l, int ff) { return DER
 __host__ __device__ inline long long split_off_dec(int layers, int ff) { return DER_FOLD_TOTAL + layers * split_layer_floats(ff); }
 __host__ __device__ inline long long derived_total(int layers, int ff) { return split_off_dec(layers, ff) + 4LL * E * E; }
 
+// ---- activations kept by elg_encode_train for the backward pass (floats; rows = B * N1) ---------------
+// per layer: xin [E] | qkv [3E] | att [E] | t1 = xin + att Wo^T + bo [E] | x1 = IN(t1) [E] | hid [ff] | t2 = x1 + ffn [E];
+// after the layers: plain fp32 score matrix E' = enc Wo-fold / sqrt(E) [rows][E].
+enum { TS_XIN = 0, TS_QKV = 1, TS_ATT = 2, TS_T1 = 3, TS_X1 = 4, TS_HID = 5, TS_T2 = 6 };
+__host__ __device__ inline long long train_layer_floats(int ff) { return 8LL * E + ff; }
+__host__ __device__ inline long long train_saved_off(int l, long long rows, int ff, int which) {
+  const long long part[7] = {0, E, 4LL * E, 5LL * E, 6LL * E, 7LL * E, 7LL * E + ff};
+  return ((long long)l * train_layer_floats(ff) + part[which]) * rows;
+}
+__host__ __device__ inline long long train_saved_eplain(int layers, long long rows, int ff) { return (long long)layers * train_layer_floats(ff) * rows; }
+__host__ __device__ inline long long train_saved_total(int layers, long long rows, int ff) { return train_saved_eplain(layers, rows, ff) + rows * E; }
+
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);

@@ -600,6 +600,7 @@ static int gemm(const float* A, const float* Bm, float* C, const float* bias, co
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+#define ELG_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 }  // namespace elg
 
@@ -614,26 +615,34 @@ size_t elg_encode_workspace_bytes(const elg_model_desc* d, int B, int N1) {
   return align_up(rows * (size_t)(E * 4 + 3 * E + d->ff) * sizeof(float), 256) + 256;
 }
 
-#define ELG_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-int elg_encode(const elg_model_desc* d, const float* weights, const float* derived, const elg_tables* t, int B,
-               int N1, void* workspace, size_t workspace_bytes, void* stream) {
+// Shared body of elg_encode / elg_encode_train.  With `saved` != NULL every layer keeps its activations
+// (layout: train_saved_* in common.cuh) for elg_reinforce_backward instead of reusing one workspace.
+static int encode_impl(const elg_model_desc* d, const float* weights, const float* derived, const elg_tables* t, int B,
+                       int N1, void* workspace, size_t workspace_bytes, float* saved, void* stream) {
   elg_weight_layout_t L;
   ELG_TRY(elg_weight_layout(d, &L));
-  ELG_REQUIRE(weights && derived && t && workspace, ELG_EINVAL, "NULL pointer");
+  ELG_REQUIRE(weights && derived && t && (workspace || saved), ELG_EINVAL, "NULL pointer");
   ELG_REQUIRE(B > 0 && N1 > 1, ELG_EINVAL, "bad batch/node count");
   ELG_REQUIRE(t->xy && t->enc && t->k && t->v && t->e && t->eb && t->qtab, ELG_EINVAL, "elg_tables has NULL members");
   ELG_REQUIRE(d->problem == ELG_TSP ? t->qfirst != nullptr : t->demand != nullptr, ELG_EINVAL,
               "tsp needs qfirst, cvrp needs demand");
-  ELG_REQUIRE(workspace_bytes >= elg_encode_workspace_bytes(d, B, N1), ELG_ENOMEM, "workspace too small");
+  ELG_REQUIRE(saved || workspace_bytes >= elg_encode_workspace_bytes(d, B, N1), ELG_ENOMEM, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)B * N1;
-  float* x = reinterpret_cast<float*>(align_up((size_t)workspace, 256));
-  float* x1 = x + rows * E;
-  float* tt = x1 + rows * E;
-  float* att = tt + rows * E;
-  float* qkv = att + rows * E;
-  float* hid = qkv + rows * 3 * E;
+  float *x, *x1, *tt, *att, *qkv, *hid, *tt2;
+  if (saved) {
+    x = saved + train_saved_off(0, rows, d->ff, TS_XIN);
+    x1 = tt = att = qkv = hid = tt2 = nullptr;
+  } else {
+    x = reinterpret_cast<float*>(align_up((size_t)workspace, 256));
+    x1 = x + rows * E;
+    tt = x1 + rows * E;
+    att = tt + rows * E;
+    qkv = att + rows * E;
+    hid = qkv + rows * 3 * E;
+    tt2 = tt;
+  }
   const float* w = weights;
 
   {
@@ -651,6 +660,16 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
   for (int l = 0; l < d->layers; ++l) {
     const auto& y = L.layer[l];
     float* xout = (l == d->layers - 1) ? t->enc : x;
+    if (saved) {
+      x = saved + train_saved_off(l, rows, d->ff, TS_XIN);
+      qkv = saved + train_saved_off(l, rows, d->ff, TS_QKV);
+      att = saved + train_saved_off(l, rows, d->ff, TS_ATT);
+      tt = saved + train_saved_off(l, rows, d->ff, TS_T1);
+      x1 = saved + train_saved_off(l, rows, d->ff, TS_X1);
+      hid = saved + train_saved_off(l, rows, d->ff, TS_HID);
+      tt2 = saved + train_saved_off(l, rows, d->ff, TS_T2);
+      if (l < d->layers - 1) xout = saved + train_saved_off(l + 1, rows, d->ff, TS_XIN);
+    }
     const long long so = split_off_layer(l, d->ff);
     ELG_TRY(tc_gemm<EPI_NONE>(x, derived, so, qkv, nullptr, nullptr, rows, 3 * E, E, 3 * E, st));
     if (N1 <= 112) enc_attention_tc_kernel<<<(unsigned)(B * H), 128, 0, st>>>(qkv, N1, att);
@@ -660,8 +679,8 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
     instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n1w, w + y.n1b, N1, x1);
     ELG_LAUNCH_OK();
     ELG_TRY(tc_gemm<EPI_BIAS_RELU>(x1, derived, so + 4LL * E * E, hid, w + y.b1, nullptr, rows, d->ff, E, d->ff, st));
-    ELG_TRY(tc_gemm<EPI_BIAS_RES>(hid, derived, so + 4LL * E * E + (long long)d->ff * E, tt, w + y.b2, x1, rows, E, d->ff, E, st));
-    instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n2w, w + y.n2b, N1, xout);
+    ELG_TRY(tc_gemm<EPI_BIAS_RES>(hid, derived, so + 4LL * E * E + (long long)d->ff * E, tt2, w + y.b2, x1, rows, E, d->ff, E, st));
+    instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt2, w + y.n2w, w + y.n2b, N1, xout);
     ELG_LAUNCH_OK();
   }
   // decoder-side tables from the encoded nodes
@@ -683,7 +702,27 @@ int elg_encode(const elg_model_desc* d, const float* weights, const float* deriv
   row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
   ELG_LAUNCH_OK();
   if (t->nbr) ELG_TRY(launch_neighbours(d, t->xy, B, N1, t->nbr, st));
+  if (saved)   // plain fp32 E' = enc (Wo/sqrt(E)) for the backward's forward recompute
+    ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WET, saved + train_saved_eplain(d->layers, rows, d->ff), nullptr, nullptr, rows, E, E, E, N1, st));
   return ELG_OK;
+}
+
+int elg_encode(const elg_model_desc* d, const float* weights, const float* derived, const elg_tables* t, int B,
+               int N1, void* workspace, size_t workspace_bytes, void* stream) {
+  ELG_REQUIRE(workspace, ELG_EINVAL, "NULL workspace");
+  return encode_impl(d, weights, derived, t, B, N1, workspace, workspace_bytes, nullptr, stream);
+}
+
+size_t elg_train_saved_bytes(const elg_model_desc* d, int B, int N1) {
+  if (check_desc(d) || B <= 0 || N1 <= 0) return 0;
+  return (size_t)train_saved_total(d->layers, (long long)B * N1, d->ff) * sizeof(float);
+}
+
+int elg_encode_train(const elg_model_desc* d, const float* weights, const float* derived, const elg_tables* t, int B,
+                     int N1, void* saved, size_t saved_bytes, void* stream) {
+  ELG_REQUIRE(saved && ((size_t)saved & 15) == 0, ELG_EINVAL, "saved-activation buffer must be 16-byte aligned");
+  ELG_REQUIRE(saved_bytes >= elg_train_saved_bytes(d, B, N1), ELG_ENOMEM, "saved-activation buffer too small");
+  return encode_impl(d, weights, derived, t, B, N1, nullptr, 0, reinterpret_cast<float*>(saved), stream);
 }
 
 }  // extern "C"

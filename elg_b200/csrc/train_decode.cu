@@ -1,0 +1,741 @@
+// Backward of the decode step (training path): replay of the recorded tours, forward recompute and gradient of
+// one decode step per POMO row, for every step of the rollout.
+//
+// reference (what is differentiated): CVRP_Decoder.forward CVRP/models.py:322-423, local_policy_att.forward
+// CVRP/models.py:51-175 (TSP/models.py:244-303, 48-110), driven by J.backward() of CVRP/train.py:112-124.
+//
+// Row-steps are independent, so the work is split into kernels without cross-row communication that write small
+// per-row-step vectors to HBM, and batched GEMMs (train_bwd.cu) that contract them over the rows of an instance:
+//   replay_kernel        tours -> per (instance, step, row) state {cur, load, mask bits, action}
+//   local_kernel<FWD>    penalty + local-policy score per node            -> ADD[row][node]
+//   global_bwd_kernel    q, attention, score, softmax; d logits -> DX, DO, DS and the query-table gradient
+//   local_kernel<BWD>    gradient of the local policy (register accumulators, flushed once per warp)
+//   local_fold_bwd       chain rule through the constant-query folds -> gradients of the local policy's parameters
+#include "train.cuh"
+#include "umma.cuh"
+
+namespace elg {
+
+constexpr unsigned FULLM = 0xffffffffu;
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULLM, v, o));
+  return v;
+}
+
+// ---- replay: the environment (CVRPEnv.step CVRP/CVRPEnv.py:190-249, TSPEnv.step TSP/TSPEnv.py:108-133) driven by the
+// recorded actions; one thread per POMO row.  Same fp32 load recurrence and masks as phase C of the rollout kernels.
+__global__ void replay_kernel(int problem, const float* __restrict__ demand, const int16_t* __restrict__ tours,
+                              int t_max, int B, int M, int N1, int T, StepRec* __restrict__ rec) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B * M) return;
+  const int b = g / M, m = g % M;
+  const bool cvrp = problem == ELG_CVRP;
+  const float* dem = cvrp ? demand + (size_t)b * N1 : nullptr;
+  const int16_t* tour = tours + (size_t)g * t_max;
+  const int W = (N1 + 31) / 32;
+  uint32_t vis[4] = {0, 0, 0, 0}, msk[4] = {0, 0, 0, 0};
+  float load = 1.f;
+  bool fin = false;
+  int cur = 0, first = 0;
+  const int tpol = cvrp ? 2 : 1;
+  for (int t = 0; t < T; ++t) {
+    const int act = t < t_max ? (int)tour[t] : 0;
+    StepRec r;
+    r.cur = cur;
+    r.act = act;
+    r.load = cvrp ? load : __int_as_float(first);
+    int open = 0;
+    for (int w = 0; w < W; ++w) {
+      const int nb = N1 - w * 32;
+      const uint32_t fullw = nb >= 32 ? FULLM : ((1u << nb) - 1u);
+      open += __popc(~msk[w] & fullw);
+    }
+    r.active = (t >= tpol && !fin && open >= 2) ? 1 : 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) r.mask[w] = msk[w];
+    rec[((size_t)b * T + t) * M + m] = r;
+    // environment step
+    if (cvrp) {
+      const bool at_depot = act == 0;
+      load = at_depot ? 1.f : load - dem[act];
+      vis[act >> 5] |= 1u << (act & 31);
+      vis[0] = at_depot ? (vis[0] | 1u) : (vis[0] & ~1u);
+      bool allv = true;
+      for (int w = 0; w < W; ++w) {
+        uint32_t big = 0;
+        for (int i = 0; i < 32; ++i) {
+          const int j = w * 32 + i;
+          if (j < N1 && __fadd_rn(load, 1e-6f) < dem[j]) big |= 1u << i;
+        }
+        const int nb = N1 - w * 32;
+        const uint32_t fullw = nb >= 32 ? FULLM : ((1u << nb) - 1u);
+        allv = allv && ((vis[w] & fullw) == fullw);
+        msk[w] = vis[w] | big;
+      }
+      fin = fin || allv;
+      if (fin) msk[0] &= ~1u;
+    } else {
+      if (t == 0) first = act;
+      vis[act >> 5] |= 1u << (act & 31);
+      msk[act >> 5] = vis[act >> 5];
+    }
+    cur = act;
+  }
+}
+
+int launch_replay(int problem, const float* demand, const int16_t* tours, int t_max, int B, int M, int N1, int T,
+                  StepRec* rec, cudaStream_t st) {
+  replay_kernel<<<(B * M + 127) / 128, 128, 0, st>>>(problem, demand, tours, t_max, B, M, N1, T, rec);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+// =================================================================================================================
+// Local policy, one warp per row-step.  Position p of the local sequence lives on lane p (and p + 32); channel c of
+// the 32-wide local embedding lives on lane c; small per-warp shared-memory vectors move data between the two views.
+//   ik_p = We f_p + be + PE(p);  s_hp = u_h . f_p + t_hp (constant query folded, log2 domain);  w_h = softmax_p
+//   ikbar_h = sum_p w_hp ik_p = We fbar_h + be + sum_p w_hp PE(p);  o = Wv[head rows] ikbar_h;  mh = Wo o + bo
+//   loc_p = mh . ik_p / sqrt(32) = (z . f_p + c0 + mh . PE(p)) / sqrt(32),  z = We^T mh, c0 = be . mh
+// =================================================================================================================
+constexpr int LW = 8;          // warps per CTA
+constexpr int PS = 33;         // padded row stride of 32-wide tables
+
+struct LocalSmem {
+  float We[LE][4];
+  float be[LE];
+  float PE[KT_MAX][PS];
+  float Wv[LE][PS];
+  float Wo[LE][PS];
+  float bo[LE];
+  float u2[LH][4];
+  float t2[LH][KT_MAX];
+  // per warp
+  float wl[LW][LH][KT_MAX];
+  float ikb[LW][LH][PS];
+  float dikb[LW][LH][PS];
+  float vo[LW][LE];
+  float vmh[LW][LE];
+  float vdmh[LW][LE];
+  float vdo[LW][LE];
+  float vg[LW][KT_MAX];
+  int ids[LW][KT_MAX];
+};
+
+template <bool CVRP, bool BWD>
+__global__ void __launch_bounds__(LW * 32) local_kernel(DecodeBwdArgs A) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  LocalSmem& S = *reinterpret_cast<LocalSmem*>(smraw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int DEP = CVRP ? 1 : 0;
+  constexpr int F = CVRP ? 3 : 2;
+  const float* w = A.weights;
+  const float* loc = A.derived + DER_LOC;
+  for (int i = tid; i < LE * 4; i += LW * 32) { const int c = i >> 2, f = i & 3; S.We[c][f] = f < F ? w[A.L.loc_we + c * F + f] : 0.f; }
+  for (int i = tid; i < LE; i += LW * 32) { S.be[i] = w[A.L.loc_be + i]; S.bo[i] = w[A.L.loc_bo + i]; }
+  for (int i = tid; i < KT_MAX * LE; i += LW * 32) S.PE[i / LE][i % LE] = loc[LOC_PE + i];
+  for (int i = tid; i < LE * LE; i += LW * 32) { S.Wv[i / LE][i % LE] = w[A.L.loc_wv + i]; S.Wo[i / LE][i % LE] = w[A.L.loc_wo + i]; }
+  for (int i = tid; i < LH * 4; i += LW * 32) S.u2[i >> 2][i & 3] = loc[LOC_U + i];
+  for (int i = tid; i < LH * KT_MAX; i += LW * 32) S.t2[i / KT_MAX][i % KT_MAX] = loc[LOC_T + i];
+  __syncthreads();
+
+  const int N1 = A.N1, NP = A.NP, M = A.M, NL = N1 - DEP, kloc = A.k_local;
+  const float isl = 0.17677669529663687f;   // 1 / sqrt(LE)
+  // gradient accumulators (BWD): lane = output row / channel
+  float aWo[LE], aWv[LE];
+  float aBo = 0.f, aWe[4] = {0.f, 0.f, 0.f, 0.f}, aDu[LH][3], aDt[LH][2];
+  if (BWD) {
+#pragma unroll
+    for (int c = 0; c < LE; ++c) aWo[c] = aWv[c] = 0.f;
+#pragma unroll
+    for (int h = 0; h < LH; ++h) { aDu[h][0] = aDu[h][1] = aDu[h][2] = 0.f; aDt[h][0] = aDt[h][1] = 0.f; }
+  }
+  const long long total = (long long)A.B * A.nT * M;
+  const int hl = lane >> 3;     // head of output row `lane`
+  for (long long item = (long long)blockIdx.x * LW + warp; item < total; item += (long long)gridDim.x * LW) {
+    const int m = (int)(item % M);
+    const int tl = (int)((item / M) % A.nT);
+    const int b = (int)(item / ((long long)M * A.nT));
+    const StepRec rc = A.rec[((size_t)b * A.T + A.t0 + tl) * M + m];
+    if (!rc.active) continue;
+    const int cur = rc.cur;
+    const uint8_t* nrow = reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_NODE_BYTES(N1);
+    const float2* feat = reinterpret_cast<const float2*>(nrow + ELG_NBR_STRIDE);
+    // ---- neighbour walk: first k unmasked entries of the distance-sorted list of `cur`
+    int cnt = 0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = lane + 32 * i;
+      int id = 0;
+      bool valid = false;
+      if (e < NL) {
+        id = nrow[nbr_pos(e)];
+        valid = !((rc.mask[id >> 5] >> (id & 31)) & 1u);
+      }
+      const uint32_t bal = __ballot_sync(FULLM, valid);
+      const int rank = cnt + __popc(bal & ((1u << lane) - 1u));
+      if (valid && rank < kloc) S.ids[warp][rank + DEP] = id;
+      cnt += __popc(bal);
+    }
+    const int kk = min(cnt, kloc);
+    const int np = kk + DEP;
+    if (DEP && lane == 0) S.ids[warp][0] = 0;
+    __syncwarp();
+    float dmax = 0.f;
+    if (kk > 0) dmax = __ldg(feat + S.ids[warp][kk - 1 + DEP]).x;
+    const float r0d = CVRP ? (dmax != 0.f ? 1.f / (dmax + 1e-6f) : 1.f) : 1.f / (dmax + 1e-6f);
+    const float r1d = dmax != 0.f ? 1.f / dmax : 1.f;
+    const float rld = CVRP ? 1.f / rc.load : 0.f;
+    const bool dep_masked = DEP && (rc.mask[0] & 1u);
+    // ---- features of this lane's positions
+    float f0[2], f1[2], f2[2], pen[2];
+    int node[2];
+    bool live[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int p = lane + 32 * s;
+      f0[s] = f1[s] = f2[s] = pen[s] = 0.f;
+      node[s] = 0;
+      live[s] = p < np;
+      if (live[s] && !(DEP && p == 0)) {
+        const int nd = S.ids[warp][p];
+        node[s] = nd;
+        const float2 ft = __ldg(feat + nd);
+        f0[s] = ft.x * r0d;
+        f1[s] = ft.y;
+        if (CVRP) {
+          pen[s] = -(ft.x * r1d);
+          f2[s] = A.t.demand[(size_t)b * N1 + nd] * rld;
+        } else {
+          pen[s] = -f0[s];
+        }
+      }
+    }
+    // ---- attention of the constant query
+    float wgt[LH][2], fbar[LH][3];
+#pragma unroll
+    for (int h = 0; h < LH; ++h) {
+      float sc[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int p = lane + 32 * s;
+        float v = -INFINITY;
+        if (live[s]) {
+          v = fmaf(S.u2[h][2], f2[s], fmaf(S.u2[h][1], f1[s], S.u2[h][0] * f0[s])) + S.t2[h][p];
+          if (DEP && p == 0 && dep_masked) v = -INFINITY;
+        }
+        sc[s] = v;
+      }
+      const float mx = warp_max(fmaxf(sc[0], sc[1]));
+      const float mref = mx == -INFINITY ? 0.f : mx;
+      const float e0 = exp2f(sc[0] - mref), e1 = exp2f(sc[1] - mref);
+      const float sum = warp_sum(e0 + e1);
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      wgt[h][0] = e0 * inv;
+      wgt[h][1] = e1 * inv;
+      S.wl[warp][h][lane] = wgt[h][0];
+      S.wl[warp][h][lane + 32] = wgt[h][1];
+      fbar[h][0] = warp_sum(wgt[h][0] * f0[0] + wgt[h][1] * f0[1]);
+      fbar[h][1] = warp_sum(wgt[h][0] * f1[0] + wgt[h][1] * f1[1]);
+      fbar[h][2] = warp_sum(wgt[h][0] * f2[0] + wgt[h][1] * f2[1]);
+    }
+    __syncwarp();
+    // ikbar_h[c], lane = c
+    float ikb[LH];
+    {
+      float acc[LH] = {0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < np; ++p) {
+        const float pe = S.PE[p][lane];
+#pragma unroll
+        for (int h = 0; h < LH; ++h) acc[h] = fmaf(S.wl[warp][h][p], pe, acc[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < LH; ++h) {
+        ikb[h] = fmaf(S.We[lane][2], fbar[h][2], fmaf(S.We[lane][1], fbar[h][1], S.We[lane][0] * fbar[h][0])) + S.be[lane] + acc[h];
+        S.ikb[warp][h][lane] = ikb[h];
+      }
+    }
+    __syncwarp();
+    // o[r], lane = r = h * 8 + d
+    float ov = 0.f;
+#pragma unroll
+    for (int c = 0; c < LE; ++c) ov = fmaf(S.Wv[lane][c], S.ikb[warp][hl][c], ov);
+    S.vo[warp][lane] = ov;
+    __syncwarp();
+    float mh = S.bo[lane];
+#pragma unroll
+    for (int c = 0; c < LE; ++c) mh = fmaf(S.Wo[lane][c], S.vo[warp][c], mh);
+    S.vmh[warp][lane] = mh;
+    __syncwarp();
+    const float z0 = warp_sum(mh * S.We[lane][0]), z1 = warp_sum(mh * S.We[lane][1]), z2 = warp_sum(mh * S.We[lane][2]);
+    const float c0 = warp_sum(mh * S.be[lane]);
+    float locv[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int p = min(lane + 32 * s, KT_MAX - 1);
+      float pm = 0.f;
+#pragma unroll
+      for (int c = 0; c < LE; ++c) pm = fmaf(S.vmh[warp][c], S.PE[p][c], pm);
+      locv[s] = (fmaf(z2, f2[s], fmaf(z1, f1[s], z0 * f0[s])) + c0 + pm) * isl;
+    }
+    const size_t row = ((size_t)b * A.nT + tl) * M + m;
+    if (!BWD) {
+      float* add = A.add + row * NP;
+      for (int j = lane; j < NP; j += 32) add[j] = (DEP && j == 0) ? 0.f : A.xi;
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (live[s]) add[node[s]] = pen[s] + locv[s];
+      continue;
+    }
+    // =========================== backward ===========================
+    const float* dxr = A.dx + row * NP;
+    float g[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      g[s] = live[s] ? dxr[node[s]] * isl : 0.f;
+      S.vg[warp][lane + 32 * s] = g[s];
+    }
+    const float dz0 = warp_sum(g[0] * f0[0] + g[1] * f0[1]);
+    const float dz1 = warp_sum(g[0] * f1[0] + g[1] * f1[1]);
+    const float dz2 = warp_sum(g[0] * f2[0] + g[1] * f2[1]);
+    const float dc0 = warp_sum(g[0] + g[1]);
+    __syncwarp();
+    // d mh[c], lane = c
+    float dmh = fmaf(S.We[lane][2], dz2, fmaf(S.We[lane][1], dz1, S.We[lane][0] * dz0)) + S.be[lane] * dc0;
+    for (int p = 0; p < np; ++p) dmh = fmaf(S.vg[warp][p], S.PE[p][lane], dmh);
+    aWe[0] = fmaf(mh, dz0, aWe[0]); aWe[1] = fmaf(mh, dz1, aWe[1]); aWe[2] = fmaf(mh, dz2, aWe[2]); aWe[3] = fmaf(mh, dc0, aWe[3]);
+    aBo += dmh;
+#pragma unroll
+    for (int c = 0; c < LE; ++c) aWo[c] = fmaf(dmh, S.vo[warp][c], aWo[c]);
+    S.vdmh[warp][lane] = dmh;
+    __syncwarp();
+    float dov = 0.f;      // d o[c], lane = c
+#pragma unroll
+    for (int k = 0; k < LE; ++k) dov = fmaf(S.Wo[k][lane], S.vdmh[warp][k], dov);
+    S.vdo[warp][lane] = dov;
+#pragma unroll
+    for (int c = 0; c < LE; ++c) aWv[c] = fmaf(dov, S.ikb[warp][hl][c], aWv[c]);
+    __syncwarp();
+    float dikb[LH], dfb[LH][3];
+#pragma unroll
+    for (int h = 0; h < LH; ++h) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < LD; ++d) a = fmaf(S.Wv[h * LD + d][lane], S.vdo[warp][h * LD + d], a);
+      dikb[h] = a;
+      S.dikb[warp][h][lane] = a;
+      aWe[0] = fmaf(a, fbar[h][0], aWe[0]); aWe[1] = fmaf(a, fbar[h][1], aWe[1]); aWe[2] = fmaf(a, fbar[h][2], aWe[2]);
+      aWe[3] += a;
+      dfb[h][0] = warp_sum(S.We[lane][0] * a);
+      dfb[h][1] = warp_sum(S.We[lane][1] * a);
+      dfb[h][2] = warp_sum(S.We[lane][2] * a);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < LH; ++h) {
+      float dw[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int p = min(lane + 32 * s, KT_MAX - 1);
+        float a = fmaf(dfb[h][2], f2[s], fmaf(dfb[h][1], f1[s], dfb[h][0] * f0[s]));
+#pragma unroll
+        for (int c = 0; c < LE; ++c) a = fmaf(S.dikb[warp][h][c], S.PE[p][c], a);
+        dw[s] = a;
+      }
+      const float wbar = warp_sum(wgt[h][0] * dw[0] + wgt[h][1] * dw[1]);
+      const float ds0 = wgt[h][0] * (dw[0] - wbar), ds1 = wgt[h][1] * (dw[1] - wbar);
+      aDt[h][0] += ds0;
+      aDt[h][1] += ds1;
+      aDu[h][0] += warp_sum(ds0 * f0[0] + ds1 * f0[1]);
+      aDu[h][1] += warp_sum(ds0 * f1[0] + ds1 * f1[1]);
+      aDu[h][2] += warp_sum(ds0 * f2[0] + ds1 * f2[1]);
+    }
+  }
+  if (BWD) {
+    float* lg = A.lg;
+#pragma unroll
+    for (int c = 0; c < LE; ++c) {
+      atomicAdd(lg + LG_WO + lane * LE + c, aWo[c]);
+      atomicAdd(lg + LG_WV + lane * LE + c, aWv[c]);
+    }
+    atomicAdd(lg + LG_BO + lane, aBo);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) atomicAdd(lg + LG_WE + lane * 4 + f, aWe[f]);
+    atomicAdd(lg + LG_BE + lane, aWe[3]);
+#pragma unroll
+    for (int h = 0; h < LH; ++h) {
+      atomicAdd(lg + LG_DT + h * KT_MAX + lane, aDt[h][0]);
+      atomicAdd(lg + LG_DT + h * KT_MAX + lane + 32, aDt[h][1]);
+      if (lane < 3) atomicAdd(lg + LG_DU + h * 4 + lane, lane == 0 ? aDu[h][0] : (lane == 1 ? aDu[h][1] : aDu[h][2]));
+    }
+  }
+}
+
+int launch_local(const DecodeBwdArgs& a, bool bwd, cudaStream_t st) {
+  const size_t smem = sizeof(LocalSmem);
+  static bool attr = false;
+  if (!attr) {
+    ELG_CUDA_OK(cudaFuncSetAttribute(local_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ELG_CUDA_OK(cudaFuncSetAttribute(local_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ELG_CUDA_OK(cudaFuncSetAttribute(local_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ELG_CUDA_OK(cudaFuncSetAttribute(local_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const long long total = (long long)a.B * a.nT * a.M;
+  long long want = (total + LW - 1) / LW;
+  const int grid = (int)(want < 148 * 4 ? want : 148 * 4);
+  const bool cvrp = a.problem == ELG_CVRP;
+  if (cvrp && !bwd) local_kernel<true, false><<<grid, LW * 32, smem, st>>>(a);
+  else if (cvrp && bwd) local_kernel<true, true><<<grid, LW * 32, smem, st>>>(a);
+  else if (!bwd) local_kernel<false, false><<<grid, LW * 32, smem, st>>>(a);
+  else local_kernel<false, true><<<grid, LW * 32, smem, st>>>(a);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+// =================================================================================================================
+// Global policy: one CTA per (instance, step), K', V, E' of the instance staged in shared memory (row stride 132
+// floats: conflict-free both for "lane = node" row reads and "lane = 4 channels" column sweeps); one warp per row.
+// =================================================================================================================
+constexpr int GW = 8;          // warps per CTA
+constexpr int GS = 132;        // table row stride (floats)
+constexpr int WS = 113;        // stride of the per-head softmax-weight rows (odd: heads land in different banks)
+
+__device__ __forceinline__ float dot16(const float* __restrict__ a, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 x = *reinterpret_cast<const float4*>(a + 4 * i);
+    const float4 y = *reinterpret_cast<const float4*>(b + 4 * i);
+    s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+  }
+  return s;
+}
+
+template <bool CVRP>
+__global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
+  extern __shared__ __align__(16) float gsm[];
+  const int N1 = A.N1, NP = A.NP, M = A.M;
+  float* sK = gsm;
+  float* sV = sK + N1 * GS;
+  float* sE = sV + N1 * GS;
+  float* seb = sE + N1 * GS;            // [128]
+  float* swl = seb + 128;               // [128]
+  float* pw = swl + 128;                // per warp: sq[128] so[128] sdo[128] sdx[128] sw[H][WS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / A.nT, tl = blockIdx.x % A.nT;
+  constexpr int PWF = 4 * 128 + H * WS;
+  float* sq = pw + warp * PWF;
+  float* so = sq + 128;
+  float* sdo = so + 128;
+  float* sdx = sdo + 128;
+  float* sw = sdx + 128;
+
+  // any active row in this (instance, step)?  (uniform over the CTA)
+  const StepRec* recs = A.rec + ((size_t)b * A.T + A.t0 + tl) * M;
+  int any = 0;
+  for (int m = tid; m < M; m += GW * 32) any |= recs[m].active;
+  any = __syncthreads_or(any);
+  const size_t row0 = ((size_t)b * A.nT + tl) * M;
+  if (!any) {
+    // the batched GEMMs read every row of the chunk: zero this CTA's rows
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < (size_t)M * E / 4; i += GW * 32) {
+      reinterpret_cast<float4*>(A.q + row0 * E)[i] = z4;
+      reinterpret_cast<float4*>(A.o + row0 * E)[i] = z4;
+      reinterpret_cast<float4*>(A.dout + row0 * E)[i] = z4;
+    }
+    for (size_t i = tid; i < (size_t)M * NP / 4; i += GW * 32) reinterpret_cast<float4*>(A.dx + row0 * NP)[i] = z4;
+    for (size_t i = tid; i < (size_t)M * H * NP / 4; i += GW * 32) {
+      reinterpret_cast<float4*>(A.w + row0 * H * NP)[i] = z4;
+      reinterpret_cast<float4*>(A.ds + row0 * H * NP)[i] = z4;
+    }
+    return;
+  }
+  {
+    const float* gk = A.t.k + (size_t)b * N1 * E;
+    const float* gv = A.t.v + (size_t)b * N1 * E;
+    const float* ge = A.eplain + (size_t)b * N1 * E;
+    for (int i = tid; i < N1 * (E / 4); i += GW * 32) {
+      const int j = i >> 5, c = (i & 31) * 4;
+      *reinterpret_cast<float4*>(sK + j * GS + c) = *reinterpret_cast<const float4*>(gk + j * E + c);
+      *reinterpret_cast<float4*>(sV + j * GS + c) = *reinterpret_cast<const float4*>(gv + j * E + c);
+      *reinterpret_cast<float4*>(sE + j * GS + c) = *reinterpret_cast<const float4*>(ge + j * E + c);
+    }
+    for (int i = tid; i < 128; i += GW * 32) {
+      seb[i] = i < N1 ? A.t.eb[(size_t)b * N1 + i] : 0.f;
+      swl[i] = A.derived[DER_WL + i];
+    }
+  }
+  __syncthreads();
+  const int c4 = lane * 4, hl = lane >> 2;
+  float4 dwl_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float ln2 = 0.6931471805599453f;
+  for (int m = warp; m < M; m += GW) {
+    const size_t row = row0 + m;
+    const StepRec rc = recs[m];
+    float* gq = A.q + row * E;
+    float* go = A.o + row * E;
+    float* gdo = A.dout + row * E;
+    float* gdx = A.dx + row * NP;
+    float* gw = A.w + row * H * NP;
+    float* gds = A.ds + row * H * NP;
+    if (!rc.active) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(gq + c4) = z4;
+      *reinterpret_cast<float4*>(go + c4) = z4;
+      *reinterpret_cast<float4*>(gdo + c4) = z4;
+      for (int j = lane; j < NP; j += 32) gdx[j] = 0.f;
+      for (int j = lane; j < H * NP; j += 32) { gw[j] = 0.f; gds[j] = 0.f; }
+      continue;
+    }
+    const int cur = rc.cur;
+    const float load = CVRP ? rc.load : 0.f;
+    const int first = CVRP ? 0 : __float_as_int(rc.load);
+    // ---- query (CVRP/models.py:336-340: Wq_last [enc[cur]; load]; TSP/models.py:258-260: q_first + Wq_last enc[cur])
+    float4 q4 = *reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + c4);
+    if (CVRP) {
+      const float4 wl4 = *reinterpret_cast<const float4*>(swl + c4);
+      q4.x = fmaf(load, wl4.x, q4.x); q4.y = fmaf(load, wl4.y, q4.y); q4.z = fmaf(load, wl4.z, q4.z); q4.w = fmaf(load, wl4.w, q4.w);
+    } else {
+      const float4 f4 = *reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + first) * E + c4);
+      q4.x += f4.x; q4.y += f4.y; q4.z += f4.z; q4.w += f4.w;
+    }
+    __syncwarp();
+    *reinterpret_cast<float4*>(sq + c4) = q4;
+    *reinterpret_cast<float4*>(gq + c4) = q4;
+    __syncwarp();
+    // ---- multi-head attention weights (log2 domain: K' carries log2(e)/sqrt(D))
+#pragma unroll 1
+    for (int h = 0; h < H; ++h) {
+      float sc[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = lane + 32 * i;
+        float s = -INFINITY;
+        if (j < N1 && !((rc.mask[i] >> lane) & 1u)) s = dot16(sq + h * D, sK + j * GS + h * D);
+        sc[i] = s;
+        mx = fmaxf(mx, s);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { sc[i] = exp2f(sc[i] - mx); sum += sc[i]; }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NP) {
+          const float wv = j < N1 ? sc[i] * inv : 0.f;
+          if (j < N1) sw[h * WS + j] = wv;
+          gw[h * NP + j] = wv;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- attention output o[c], lane = 4 channels of head hl
+    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < N1; ++j) {
+      const float wv = sw[hl * WS + j];
+      const float4 v4 = *reinterpret_cast<const float4*>(sV + j * GS + c4);
+      o4.x = fmaf(wv, v4.x, o4.x); o4.y = fmaf(wv, v4.y, o4.y); o4.z = fmaf(wv, v4.z, o4.z); o4.w = fmaf(wv, v4.w, o4.w);
+    }
+    *reinterpret_cast<float4*>(so + c4) = o4;
+    *reinterpret_cast<float4*>(go + c4) = o4;
+    __syncwarp();
+    // ---- scores, clipping, softmax over the nodes, d logits
+    float xs[4], th[4], lg[4];
+    float mx = -INFINITY;
+    const float* addr = A.add + row * NP;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = lane + 32 * i;
+      lg[i] = -INFINITY; th[i] = 0.f; xs[i] = 0.f;
+      if (j < N1 && !((rc.mask[i] >> lane) & 1u)) {
+        float s = seb[j];
+        const float* er = sE + j * GS;
+#pragma unroll 8
+        for (int c = 0; c < E; c += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(so + c);
+          const float4 e4 = *reinterpret_cast<const float4*>(er + c);
+          s = fmaf(a.x, e4.x, s); s = fmaf(a.y, e4.y, s); s = fmaf(a.z, e4.z, s); s = fmaf(a.w, e4.w, s);
+        }
+        xs[i] = s + addr[j];
+        th[i] = tanhf(xs[i]);
+        lg[i] = A.clip * th[i];
+      }
+      mx = fmaxf(mx, lg[i]);
+    }
+    mx = warp_max(mx);
+    float pe[4], sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pe[i] = __expf(lg[i] - mx); sum += pe[i]; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    const float cf = A.coef[(size_t)b * M + m];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = lane + 32 * i;
+      float dxv = 0.f;
+      if (lg[i] != -INFINITY) {
+        const float dl = cf * ((j == rc.act ? 1.f : 0.f) - pe[i] * inv);
+        dxv = dl * A.clip * (1.f - th[i] * th[i]);
+      }
+      if (j < 128) sdx[j] = dxv;
+      if (j < NP) gdx[j] = dxv;
+    }
+    __syncwarp();
+    // ---- d o = sum_j dx_j E'_j
+    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < N1; ++j) {
+      const float x = sdx[j];
+      const float4 e4 = *reinterpret_cast<const float4*>(sE + j * GS + c4);
+      d4.x = fmaf(x, e4.x, d4.x); d4.y = fmaf(x, e4.y, d4.y); d4.z = fmaf(x, e4.z, d4.z); d4.w = fmaf(x, e4.w, d4.w);
+    }
+    *reinterpret_cast<float4*>(sdo + c4) = d4;
+    *reinterpret_cast<float4*>(gdo + c4) = d4;
+    __syncwarp();
+    // ---- softmax backward per head: d s2_hj = ln2 * w_hj (d w_hj - sum_j w d w)
+#pragma unroll 1
+    for (int h = 0; h < H; ++h) {
+      float dw[4], wv[4];
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = lane + 32 * i;
+        dw[i] = 0.f; wv[i] = 0.f;
+        if (j < N1) {
+          wv[i] = sw[h * WS + j];
+          dw[i] = dot16(sdo + h * D, sV + j * GS + h * D);
+        }
+        part = fmaf(wv[i], dw[i], part);
+      }
+      const float wbar = warp_sum(part);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = lane + 32 * i;
+        if (j < NP) {
+          const float d = j < N1 ? ln2 * wv[i] * (dw[i] - wbar) : 0.f;
+          if (j < N1) sw[h * WS + j] = d;
+          gds[h * NP + j] = d;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- d q = sum_j d s2_hj K'_j ; scatter into the query-table gradient
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < N1; ++j) {
+      const float x = sw[hl * WS + j];
+      const float4 k4 = *reinterpret_cast<const float4*>(sK + j * GS + c4);
+      g4.x = fmaf(x, k4.x, g4.x); g4.y = fmaf(x, k4.y, g4.y); g4.z = fmaf(x, k4.z, g4.z); g4.w = fmaf(x, k4.w, g4.w);
+    }
+    float* dq = A.dqtab + ((size_t)b * N1 + cur) * E + c4;
+    atomicAdd(dq + 0, g4.x); atomicAdd(dq + 1, g4.y); atomicAdd(dq + 2, g4.z); atomicAdd(dq + 3, g4.w);
+    if (CVRP) {
+      dwl_acc.x = fmaf(load, g4.x, dwl_acc.x); dwl_acc.y = fmaf(load, g4.y, dwl_acc.y);
+      dwl_acc.z = fmaf(load, g4.z, dwl_acc.z); dwl_acc.w = fmaf(load, g4.w, dwl_acc.w);
+    } else {
+      float* df = A.dqfirst + ((size_t)b * N1 + first) * E + c4;
+      atomicAdd(df + 0, g4.x); atomicAdd(df + 1, g4.y); atomicAdd(df + 2, g4.z); atomicAdd(df + 3, g4.w);
+    }
+  }
+  if (CVRP) {
+    atomicAdd(A.dwl + c4 + 0, dwl_acc.x); atomicAdd(A.dwl + c4 + 1, dwl_acc.y);
+    atomicAdd(A.dwl + c4 + 2, dwl_acc.z); atomicAdd(A.dwl + c4 + 3, dwl_acc.w);
+  }
+}
+
+int launch_global_bwd(const DecodeBwdArgs& a, cudaStream_t st) {
+  const size_t smem = ((size_t)3 * a.N1 * GS + 256 + (size_t)GW * (4 * 128 + H * WS)) * sizeof(float);
+  ELG_REQUIRE(smem <= 227 * 1024, ELG_EUNSUPPORTED, "training supports up to %d nodes (needs %zu bytes of shared memory)", TRAIN_MAX_NODES, smem);
+  ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)(a.B * a.nT);
+  if (a.problem == ELG_CVRP) global_bwd_kernel<true><<<grid, GW * 32, smem, st>>>(a);
+  else global_bwd_kernel<false><<<grid, GW * 32, smem, st>>>(a);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+// =================================================================================================================
+// Chain rule through the constant-query folds of the local policy (one CTA):
+//   q = Wq token;  a_h = Wk_h^T q_h / sqrt(8);  u_h = We^T a_h;  t_hp = a_h . (be + PE(p))
+// =================================================================================================================
+__global__ void local_fold_bwd_kernel(elg_model_desc d, elg_weight_layout_t L, const float* __restrict__ w,
+                                      const float* __restrict__ der, const float* __restrict__ lg,
+                                      float* __restrict__ grads) {
+  __shared__ float q[LE], a[LH][LE], da[LH][LE], dq[LE], sdt[LH], We[LE][4];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int F = d.problem == ELG_CVRP ? 3 : 2;
+  const float isd = 0.35355339059327373f;   // 1 / sqrt(LD)
+  const float* pe = der + DER_LOC + LOC_PE;
+  for (int c = tid; c < LE; c += nt) {
+    float s = 0.f;
+    for (int i = 0; i < LE; ++i) s = fmaf(w[L.loc_wq + c * LE + i], w[L.loc_token + i], s);
+    q[c] = s;
+    for (int f = 0; f < 4; ++f) We[c][f] = f < F ? w[L.loc_we + c * F + f] : 0.f;
+  }
+  for (int h = tid; h < LH; h += nt) {
+    float s = 0.f;
+    for (int p = 0; p < KT_MAX; ++p) s += lg[LG_DT + h * KT_MAX + p];
+    sdt[h] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < LH * LE; i += nt) {
+    const int h = i / LE, c = i % LE;
+    float s = 0.f;
+    for (int dd = 0; dd < LD; ++dd) s = fmaf(w[L.loc_wk + (h * LD + dd) * LE + c], q[h * LD + dd], s);
+    a[h][c] = s * isd;
+    float g = 0.f;
+    for (int f = 0; f < 3; ++f) g = fmaf(We[c][f], lg[LG_DU + h * 4 + f], g);
+    for (int p = 0; p < KT_MAX; ++p) g = fmaf(lg[LG_DT + h * KT_MAX + p], w[L.loc_be + c] + pe[p * LE + c], g);
+    da[h][c] = g;
+  }
+  __syncthreads();
+  for (int r = tid; r < LE; r += nt) {
+    const int h = r / LD;
+    float s = 0.f;
+    for (int c = 0; c < LE; ++c) s = fmaf(w[L.loc_wk + r * LE + c], da[h][c], s);
+    dq[r] = s * isd;
+  }
+  __syncthreads();
+  for (int i = tid; i < LE * LE; i += nt) {
+    const int r = i / LE, c = i % LE, h = r / LD;
+    grads[L.loc_wk + i] += q[r] * da[h][c] * isd;
+    grads[L.loc_wq + i] += dq[r] * w[L.loc_token + c];
+    grads[L.loc_wv + i] += lg[LG_WV + i];
+    grads[L.loc_wo + i] += lg[LG_WO + i];
+  }
+  for (int c = tid; c < LE; c += nt) {
+    float s = 0.f;
+    for (int r = 0; r < LE; ++r) s = fmaf(w[L.loc_wq + r * LE + c], dq[r], s);
+    grads[L.loc_token + c] += s;
+    grads[L.loc_bo + c] += lg[LG_BO + c];
+    float gb = lg[LG_BE + c];
+    for (int h = 0; h < LH; ++h) gb = fmaf(a[h][c], sdt[h], gb);
+    grads[L.loc_be + c] += gb;
+    for (int f = 0; f < F; ++f) {
+      float g = lg[LG_WE + c * 4 + f];
+      for (int h = 0; h < LH; ++h) g = fmaf(a[h][c], lg[LG_DU + h * 4 + f], g);
+      grads[L.loc_we + c * F + f] += g;
+    }
+  }
+}
+
+int launch_local_fold_bwd(const elg_model_desc* d, const elg_weight_layout_t& L, const float* weights, const float* derived,
+                          const float* lg, float* grads, cudaStream_t st) {
+  local_fold_bwd_kernel<<<1, 256, 0, st>>>(*d, L, weights, derived, lg, grads);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
+}  // namespace elg

@@ -290,3 +290,66 @@ def tour_length(xy, tours, rounding=False):
         check(lib.elg_tour_length(_ptr(xy), int(xy.shape[0]), _ptr(t64), B, M, T, int(xy.shape[1]), 1 if rounding else 0,
                                   _ptr(out), _stream(tours.device)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- training path
+def encode_train(handle, xy, demand=None):
+    """model.pre_forward for a training step: elg_encode that also keeps every layer's activations.
+    Returns (EncodedBatch, saved-activation buffer)."""
+    batch = EncodedBatch(handle, xy, demand, None)
+    dev = batch.xy.device
+    nbytes = int(lib.elg_train_saved_bytes(handle.desc, batch.B, batch.N1))
+    saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.elg_encode_train(handle.desc, _ptr(handle.weights), _ptr(handle.derived), batch.tables, batch.B, batch.N1,
+                                   _ptr(saved), nbytes, _stream(dev)))
+    return batch, saved
+
+
+_train_ws = {}
+
+
+def reinforce_backward(batch, saved, M, tours, T, reward, logp=None, scale_norm=True, chunk_steps=16, grads=None):
+    """J.backward() of the reference's training step (CVRP/train.py:112-124) for the recorded rollout.
+    Returns (grads packed like handle.weights, loss (1,) tensor, workspace tensor)."""
+    h = batch.handle
+    dev = batch.xy.device
+    B, N1 = batch.B, batch.N1
+    t_max = int(tours.shape[2])
+    nbytes = int(lib.elg_train_workspace_bytes(h.desc, B, M, N1, t_max, int(chunk_steps)))
+    if nbytes == 0:
+        raise _lib.ElgError("unsupported training shape: %s" % lib.elg_last_error().decode())
+    ws = _train_ws.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        _train_ws[dev] = None
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _train_ws[dev] = ws
+    if grads is None:
+        grads = torch.empty_like(h.weights)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.elg_reinforce_backward(h.desc, _ptr(h.weights), _ptr(h.derived), batch.tables, _ptr(saved), B, M, N1,
+                                         _ptr(tours), t_max, int(T), _ptr(reward.contiguous()), _ptr(logp), 1 if scale_norm else 0,
+                                         _ptr(grads), _ptr(loss), _ptr(ws), ws.numel(), _stream(dev)))
+    return grads, loss, ws
+
+
+def train_workspace_layout(handle, B, M, N1, t_max):
+    out = (C.c_int64 * 8)()
+    check(lib.elg_train_workspace_layout(handle.desc, B, M, N1, t_max, out))
+    names = ("dEp", "dK", "dV", "dqtab", "dqfirst", "deb", "dwl", "lg")
+    return dict(zip(names, [int(x) for x in out]))
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-6,
+              grad_scale=1.0):
+    dev = params.device
+    with torch.cuda.device(dev):
+        check(lib.elg_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), int(step),
+                                lr, beta1, beta2, eps, weight_decay, grad_scale, _stream(dev)))
+
+
+def prepare_model(handle):
+    """Re-fold the decoder / local-policy tables after the packed weights changed (optimizer step)."""
+    with torch.cuda.device(handle.device):
+        check(lib.elg_prepare_model(handle.desc, _ptr(handle.weights), _ptr(handle.derived), _stream(handle.device)))

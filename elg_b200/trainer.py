@@ -1,0 +1,83 @@
+"""REINFORCE training of ELG-POMO with the shared baseline: host side of the reference's training loop body
+(CVRP/train.py:83-148, TSP/train.py:80-146) on top of the C ABI.
+
+One `Trainer.step(batch)` = load_random_problems + pre_forward + rollout(sample) + J.backward() + Adam step.
+Data-parallel training (one process per GPU): every rank runs the step on its own instances and the packed
+gradient is summed with one NCCL all-reduce before the Adam step (grad_scale = 1 / world_size), so that equal
+shards give the gradient of the global mean of J.  There is no CPU path.
+"""
+import random
+
+import torch
+
+from . import engine
+from ._lib import ElgError
+
+
+class Trainer:
+    def __init__(self, problem, model_params, state_dict, device, lr=1e-4, weight_decay=1e-6, scale_norm=True,
+                 betas=(0.9, 0.999), eps=1e-8, chunk_steps=16, process_group=None):
+        self.problem = problem
+        self.handle = engine.ModelHandle(problem, model_params, state_dict, device, attention="fp32")
+        self.device = self.handle.device
+        self.lr, self.weight_decay, self.scale_norm, self.betas, self.eps = lr, weight_decay, scale_norm, betas, eps
+        self.chunk_steps = chunk_steps
+        self.exp_avg = torch.zeros_like(self.handle.weights)
+        self.exp_avg_sq = torch.zeros_like(self.handle.weights)
+        self.grads = torch.zeros_like(self.handle.weights)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self._slots, _ = engine.weight_slots(problem, self.handle.desc)
+        self._shapes = {k: tuple(v.shape) for k, v in state_dict.items() if k in self._slots}
+
+    # ---- one forward (sample rollout) + backward; returns the pieces so tests can look at them
+    def forward_backward(self, data, M, start_nodes=None, seed=0):
+        cv = self.problem == "cvrp"
+        if cv:
+            xy, dem = engine.load_problems("cvrp", data["loc"].to(self.device), data["depot"].to(self.device),
+                                           data["demand"].to(self.device), 1)
+        else:
+            xy, dem = engine.load_problems("tsp", data.to(self.device), None, None, 1)
+        N1 = int(xy.shape[1])
+        if start_nodes is None:      # CVRP/CVRPModel.py:47, TSP/TSPModel.py:31
+            start_nodes = random.sample(range(0, N1 - 1 if cv else M), M)
+        batch, saved = engine.encode_train(self.handle, xy, dem)
+        tours, reward, logp, n_steps = engine.rollout(batch, M, start_nodes, "sample", seed=seed)
+        T = int(n_steps.max().item())
+        grads, loss, ws = engine.reinforce_backward(batch, saved, M, tours, T, reward, logp, self.scale_norm,
+                                                    self.chunk_steps, self.grads)
+        return dict(batch=batch, tours=tours, reward=reward, logp=logp, T=T, grads=grads, loss=loss, ws=ws)
+
+    def optimizer_step(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)       # NCCL sum over NVLink
+        self.step_count += 1
+        engine.adam_step(self.handle.weights, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                         self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        engine.prepare_model(self.handle)
+
+    def step(self, data, M, start_nodes=None, seed=None):
+        if seed is None:
+            seed = (torch.initial_seed() * 1000003 + self.step_count) & (2 ** 63 - 1)
+        out = self.forward_backward(data, M, start_nodes, seed)
+        self.optimizer_step()
+        return out
+
+    # ---- reference-format state (CVRP/train.py:137-141)
+    def state_dict(self):
+        w = self.handle.weights.detach().cpu()
+        return {k: w[off:off + int(torch.tensor(self._shapes[k]).prod())].reshape(self._shapes[k]).clone()
+                for k, off in self._slots.items()}
+
+    def unpack(self, flat):
+        f = flat.detach().cpu()
+        return {k: f[off:off + int(torch.tensor(self._shapes[k]).prod())].reshape(self._shapes[k]).clone()
+                for k, off in self._slots.items()}
+
+    def checkpoint(self):
+        return {"step": self.step_count, "model_state_dict": self.state_dict(),
+                "optimizer_state_dict": {"exp_avg": self.unpack(self.exp_avg), "exp_avg_sq": self.unpack(self.exp_avg_sq),
+                                         "step": self.step_count, "lr": self.lr, "weight_decay": self.weight_decay}}

@@ -209,6 +209,37 @@ int elg_cur_feature(const float* xy, const float* demand, const float* load, con
 int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M, int T, int N1, int round_edges,
                     float* out, void* stream);
 
+/* ---- training path (REINFORCE with the POMO shared baseline) ----------------------------------
+ * Replaces the body of the reference's training loop, CVRP/train.py:104-125 (TSP/train.py:100-122):
+ *   model.pre_forward            -> elg_encode_train   (elg_encode that also keeps every layer's activations)
+ *   rollout(eval_type='sample')  -> elg_rollout(mode = ELG_SAMPLE), which records tours, rewards and sum log p
+ *   J = mean(-(r - mean_m r) * log_prob / max_m(r - mean_m r));  J.backward()
+ *                                -> elg_reinforce_backward  (gradient of J w.r.t. every parameter, packed like the
+ *                                   weight buffer of elg_weight_layout; overwritten, not accumulated)
+ *   optimizer.step()             -> elg_adam_step  (torch.optim.Adam with L2 weight decay; CVRP/train.py:87)
+ * followed by elg_prepare_model on the updated weights.  Data-parallel training all-reduces `grads` (NCCL) between
+ * elg_reinforce_backward and elg_adam_step; grad_scale = 1 / world_size turns the sum into the mean.
+ *   saved      elg_train_saved_bytes() bytes, 16-byte aligned; written by elg_encode_train
+ *   tours      [B][M][t_max] int16 as written by elg_rollout;  T = number of steps of the rollout (max n_steps)
+ *   reward     [B][M];  logp [B][M] (only used for the reported loss, may be NULL);  loss: one float (may be NULL)
+ *   scale_norm config params.scale_norm (tsp: applied only if every instance has a non-zero maximum advantage)
+ *   workspace  256-byte aligned, at least elg_train_workspace_bytes(..., chunk_steps = 1); a larger chunk_steps (up
+ *              to 32) lets the decode backward process that many rollout steps per launch.  Its head holds the
+ *              gradients of the decoder tables (float offsets from elg_train_workspace_layout: d E', d K', d V,
+ *              d qtab, d qfirst, d eb, d w_load, local-policy accumulators), left in place for inspection.
+ * Instances of up to 112 nodes (the resident variant). */
+size_t elg_train_saved_bytes(const elg_model_desc* desc, int B, int N1);
+int elg_encode_train(const elg_model_desc* desc, const float* weights, const float* derived, const elg_tables* t,
+                     int B, int N1, void* saved, size_t saved_bytes, void* stream);
+size_t elg_train_workspace_bytes(const elg_model_desc* desc, int B, int M, int N1, int t_max, int chunk_steps);
+int elg_train_workspace_layout(const elg_model_desc* desc, int B, int M, int N1, int t_max, int64_t* out8);
+int elg_reinforce_backward(const elg_model_desc* desc, const float* weights, const float* derived, const elg_tables* t,
+                           const void* saved, int B, int M, int N1, const int16_t* tours, int t_max, int T,
+                           const float* reward, const float* logp, int scale_norm, float* grads, float* loss,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int elg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------------------------
  * One split-precision tcgen05 GEMM  D[128][n] = A[rows_a][k] * B[n][k]^T  (fp16 hi/lo operands, fp32
  * accumulation in TMEM; terms = 1: hi*hi only, 3: + hi*lo + lo*hi; alias: 64-row A operand whose upper
