@@ -291,6 +291,148 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- training workload
+TRAIN_METRIC = "CVRP100 REINFORCE training instances/s (POMO=100 shared baseline, sample rollout + backward + Adam)"
+
+
+def train_config(batch_per_gpu, n_gpus):
+    return {"workload": "CVRP100 REINFORCE training step with POMO shared baseline, batch %d x 100 rollouts per GPU, "
+                        "data-parallel with one NCCL all-reduce of the packed gradient" % batch_per_gpu,
+            "problem_size": N_NODES, "pomo": POMO, "aug": 1, "instances_per_step_per_gpu": batch_per_gpu,
+            "weights": "seeded random init", "l2_policy": "fresh instances every step; per-step activations + row-step "
+            "buffers (> 1 GB) exceed L2", "parallelism": "dp%d" % n_gpus}
+
+
+def run_train(args):
+    """BASELINE.json configs[2]: one step = generate/load a batch, encoder (activations kept), sample rollout, REINFORCE
+    backward, all-reduce of the gradient (N > 1), Adam, re-fold of the decoder tables."""
+    import torch
+    import torch.distributed as dist
+    from elg_b200 import _lib
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
+    from elg_b200.trainer import Trainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    tr = Trainer("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]), synthetic_state_dict("cvrp", seed=WEIGHT_SEED), dev,
+                 chunk_steps=args.chunk_steps)
+    nb = args.train_batch
+    total_steps = args.warmup + args.steps
+    host = [{k: v.pin_memory() for k, v in make_instances(nb, INSTANCE_SEED + 7919 * s + rank).items()} for s in range(total_steps)]
+    dev_batches = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device(s):
+        random.seed(INSTANCE_SEED + s)
+        return tr.step(dev_batches[s], POMO, seed=INSTANCE_SEED + s)
+
+    def step_e2e(s):
+        random.seed(INSTANCE_SEED + s)
+        out = tr.step({k: v.to(dev, non_blocking=True) for k, v in host[s].items()}, POMO, seed=INSTANCE_SEED + s)
+        loss_host.copy_(out["loss"], non_blocking=True)
+        return out
+
+    def timed(fn):
+        for s in range(args.warmup):
+            fn(s)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        costs, Ts = [], []
+        for s in range(args.warmup, total_steps):
+            out = fn(s)
+            costs.append(-out["reward"].mean())
+            Ts.append(out["T"])
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks, [float(c) for c in costs], Ts
+
+    ms_dev, launches, clocks, costs, Ts = timed(step_device)
+    ms_e2e, _, clocks_e2e, _, _ = timed(step_e2e)
+    if rank == 0:
+        n_total = nb * world * args.steps
+        line = {"metric": TRAIN_METRIC, "value": n_total / (ms_dev * 1e-3), "unit": "instances/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(nb, world),
+                "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "instances/s",
+                        "h2d_bytes_per_step": nb * (2 + 2 * N_NODES + N_NODES) * 4, "d2h_bytes_per_step": 4 + 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "clocks_e2e": clocks_e2e,
+                "mean_sampled_cost_per_step": costs, "rollout_steps_T": Ts,
+                "grad_allreduce_bytes": int(tr.grads.numel()) * 4 if world > 1 else 0}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt, T, cores = cpu_train_rate(args.cpu_train_sample, INSTANCE_SEED)
+            line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
+                                    "sample": "%d CVRP100 instances x 100 rollouts, one step, %.1f s, T=%d; oracle port: teacher-forced "
+                                              "forward with autograd graph + backward + Adam on pre-sampled tours" % (args.cpu_train_sample, dt, T)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_train_rate(n_inst, seed):
+    """The reference's training step on host cores (oracle port): forward with autograd graph, J.backward(), Adam."""
+    import torch
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
+    from oracle import elg_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    mp = dict(DEFAULT_MODEL_PARAMS["cvrp"])
+    sd = synthetic_state_dict("cvrp", seed=WEIGHT_SEED)
+    data = make_instances(n_inst, seed)
+    prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], 1)
+    perm = O.start_permutation("cvrp", N_NODES, POMO, seed=seed)
+    with torch.no_grad():          # sampling pre-pass (not timed): fixes the action sequence
+        tours, _, reward = O.rollout(O.Weights(sd, "cvrp", mp), prob, POMO, perm, "sample", generator=torch.Generator().manual_seed(seed))
+    W = O.Weights(sd, "cvrp", mp).requires_grad_()
+    opt = torch.optim.Adam(list(W.sd.values()), lr=1e-4, weight_decay=1e-6)
+    t0 = time.perf_counter()
+    J, _ = O.reinforce_loss(W, prob, POMO, tours, reward, True)
+    opt.zero_grad()
+    J.backward()
+    opt.step()
+    dt = time.perf_counter() - t0
+    return n_inst / dt, dt, int(tours.shape[2]), torch.get_num_threads()
+
+
+def run_reference_train(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    times, T, cores = [], 0, 1
+    for s in range(args.warmup + args.steps):
+        rate, dt, T, cores = cpu_train_rate(args.cpu_train_sample, INSTANCE_SEED + s)
+        if s >= args.warmup:
+            times.append(dt)
+    value = args.cpu_train_sample * len(times) / sum(times)
+    print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": "instances/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": train_config(args.cpu_train_sample, 1),
+                      "cpu_baseline": {"value": value, "unit": "instances/s", "cores": cores, "kind": "port",
+                                       "sample": "%d CVRP100 instances x 100 rollouts per step, T=%d" % (args.cpu_train_sample, T)},
+                      "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,10 +443,17 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="instances per step for --impl reference (bounded sample)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="instances in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
+                    help="inference = BASELINE.json configs[1] (the headline metric); train = configs[2]")
+    ap.add_argument("--train-batch", type=int, default=64, help="training instances per step per GPU")
+    ap.add_argument("--chunk-steps", type=int, default=16, help="rollout steps per decode-backward launch")
+    ap.add_argument("--cpu-train-sample", type=int, default=2, help="instances in the CPU training-step sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("ELG_BENCH_ALLOW_SHORT"):
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "train":
+        run_reference_train(args) if args.impl == "reference" else run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

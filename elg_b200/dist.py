@@ -35,3 +35,14 @@ def gather_costs(local_costs, n_total):
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return torch.cat([out[r][:shard_slice(n_total, r, world).stop - shard_slice(n_total, r, world).start] for r in range(world)])
+
+
+def allreduce_mean_gradient(flat_grad, group=None):
+    """Training path: sum the packed gradient over the ranks (ONE all-reduce of the whole parameter vector, 5 MB for the
+    released model) and return the factor that turns the sum into the gradient of the global mean of J.  Every rank's J
+    is a mean over its own instances x POMO rows (CVRP/train.py:121), so with equal shards mean-of-means = global mean
+    (SURVEY 8e); the factor is applied inside elg_adam_step (grad_scale)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 1.0
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / dist.get_world_size(group)

@@ -11,7 +11,7 @@ import random
 import torch
 
 from . import engine
-from ._lib import ElgError
+from .dist import allreduce_mean_gradient
 
 
 class Trainer:
@@ -52,11 +52,10 @@ class Trainer:
         return dict(batch=batch, tours=tours, reward=reward, logp=logp, T=T, grads=grads, loss=loss, ws=ws)
 
     def optimizer_step(self):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)       # NCCL sum over NVLink
+        scale = allreduce_mean_gradient(self.grads, self.pg)              # NCCL sum over NVLink (no-op on one GPU)
         self.step_count += 1
         engine.adam_step(self.handle.weights, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
-                         self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+                         self.betas[0], self.betas[1], self.eps, self.weight_decay, scale)
         engine.prepare_model(self.handle)
 
     def step(self, data, M, start_nodes=None, seed=None):

@@ -89,7 +89,9 @@ def test_own_sampled_rollout_gradient_and_adam(kind, N):
     J, logp, ref, _ = TH.oracle_grads(kind, mp, sd, prob, M, tours, reward, True)
     assert float((out["logp"].cpu() - logp).abs().max()) < 5e-3 * max(1.0, float(logp.abs().max()))
     assert abs(float(out["loss"]) - float(J)) < 5e-3 * max(1.0, abs(float(J)))
-    eo = TH.grad_errors(tr.unpack(out["grads"]), ref)
+    # Frobenius error per tensor: on a freshly sampled rollout a ReLU pre-activation within rounding of zero may flip
+    # between our forward and the oracle's, which moves one row of that layer's gradient (seen on layers.3 W1)
+    eo = TH.grad_errors_l2(tr.unpack(out["grads"]), ref)
     assert max(eo.values()) < 2e-2, sorted(eo.items(), key=lambda kv: -kv[1])[:3]
     # Adam: compare on the packed buffer with the oracle formula applied to OUR gradient (isolates the optimizer)
     g = out["grads"].cpu()

@@ -1,48 +1,11 @@
 """CPU: the oracle's teacher-forced REINFORCE objective, its autograd gradient and its Adam step against the
 reference's own training step (tests/golden/train_*.npz, made by oracle/gen_golden_train.py)."""
-import json
-import os
-
 import numpy as np
 import pytest
 import torch
 
-from elg_b200.synth import state_dict_checksum, synthetic_state_dict
 from oracle import elg_oracle as O
-from helpers import GOLDEN
-
-TRAIN_CASES = ["train_cvrp_n20", "train_cvrp_n50", "train_cvrp_n100", "train_tsp_n20", "train_tsp_n50"]
-SAMPLE = 512
-
-
-def sample_idx(numel):
-    if numel <= SAMPLE:
-        return np.arange(numel)
-    return (np.arange(SAMPLE) * (numel // SAMPLE)).astype(np.int64)
-
-
-class TrainGolden:
-    def __init__(self, name):
-        self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
-        self.meta = json.loads(str(self.z["meta"]))
-        self.kind, self.M = self.meta["problem"], self.meta["M"]
-
-    def state_dict(self):
-        sd = synthetic_state_dict(self.kind, seed=self.meta["wseed"], gain=self.meta["gain"])
-        assert state_dict_checksum(sd) == self.meta["wsum"]
-        return sd
-
-    def problem(self, dtype=torch.float32):
-        z = self.z
-        if self.kind == "cvrp":
-            return O.load_cvrp(torch.tensor(z["depot"]), torch.tensor(z["loc"]), torch.tensor(z["demand"]), 1, dtype)
-        return O.load_tsp(torch.tensor(z["problems"]), 1, dtype)
-
-    def tours(self):
-        return torch.tensor(self.z["tours"].astype(np.int64))
-
-    def reward(self):
-        return torch.tensor(self.z["reward"])
+from train_helpers import TRAIN_CASES, TrainGolden, sample_idx
 
 
 def oracle_grads(g, dtype=torch.float32):

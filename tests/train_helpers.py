@@ -75,6 +75,15 @@ def grad_errors(mine, ref, floor_frac=1e-3):
     return {k: float((mine[k].double().cpu() - ref[k].double()).abs().max()) / max(rms[k], floor) for k in ref}
 
 
+def grad_errors_l2(mine, ref, floor_frac=1e-3):
+    """Per tensor: ||mine - ref||_F / max(||ref||_F, floor_frac * largest tensor rms * sqrt(numel)).  Robust against a
+    single ReLU unit whose pre-activation sits within rounding of zero (its whole gradient row flips on or off)."""
+    rms = {k: float(ref[k].double().norm()) / np.sqrt(ref[k].numel()) for k in ref}
+    floor = floor_frac * max(rms.values())
+    return {k: float((mine[k].double().cpu() - ref[k].double()).norm()) / (max(rms[k], floor) * np.sqrt(ref[k].numel()))
+            for k in ref}
+
+
 def fixture_errors(g, mine, floor_frac=1e-3):
     rms = {k: float(g.z["g_norm/" + k]) / np.sqrt(mine[k].numel()) for k in g.meta["keys"]}
     floor = floor_frac * max(rms.values())

@@ -60,7 +60,53 @@ def run(name, verbose=True):
     return worst
 
 
+def run_own(kind, N, n, M, gain, wseed=5):
+    """Own sampled rollout; ours and the fp32 oracle both measured against the fp64 oracle on the same tours."""
+    import random
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    from oracle import elg_oracle as O
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    sd = synthetic_state_dict(kind, seed=wseed, gain=gain)
+    tr = Trainer(kind, mp, sd, "cuda:0")
+    if kind == "cvrp":
+        data = synthetic_cvrp_batch(n, N, seed=9)
+        prob = lambda dt: O.load_cvrp(data["depot"], data["loc"], data["demand"], 1, dt)
+    else:
+        data = synthetic_tsp_batch(n, N, seed=9)
+        prob = lambda dt: O.load_tsp(data, 1, dt)
+    random.seed(4)
+    out = tr.forward_backward(data, M, seed=123)
+    torch.cuda.synchronize()
+    T = out["T"]
+    tours = out["tours"][:, :, :T].long().cpu()
+    reward = out["reward"].cpu()
+    mine = tr.unpack(out["grads"])
+    J32, lp32, g32, _ = TH.oracle_grads(kind, mp, sd, prob(torch.float32), M, tours, reward, True)
+    J64, lp64, g64, _ = TH.oracle_grads(kind, mp, sd, prob(torch.float64), M, tours, reward.double(), True, dtype=torch.float64)
+    e_m = TH.grad_errors(mine, g64)
+    e_o = TH.grad_errors(g32, g64)
+    print("== own %s N=%d n=%d M=%d gain=%.1f T=%d: J ours %.6f fp32 %.6f fp64 %.6f; logp err ours %.2e fp32 %.2e" % (
+        kind, N, n, M, gain, T, float(out["loss"]), float(J32), float(J64),
+        float((out["logp"].cpu().double() - lp64).abs().max()), float((lp32.double() - lp64).abs().max())))
+    for k in sorted(e_m, key=lambda k: -e_m[k])[:8]:
+        print("   %-58s ours vs fp64 %.2e   fp32 oracle vs fp64 %.2e" % (k, e_m[k], e_o[k]))
+    l2 = TH.grad_errors_l2(mine, g64)
+    print("   worst Frobenius error: %s" % str(sorted(l2.items(), key=lambda kv: -kv[1])[:3]))
+    k = max(e_m, key=lambda k: e_m[k])
+    d = (mine[k].double() - g64[k]).abs()
+    if d.dim() == 2:
+        rowerr = d.pow(2).sum(1)
+        top = rowerr.topk(3)
+        print("   %s: error energy by output row: top3 rows %s hold %.1f%% of the squared error" % (
+            k, top.indices.tolist(), 100 * float(top.values.sum() / rowerr.sum())))
+    return max(e_m.values())
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["train_cvrp_n20"]
-    w = [run(n) for n in names]
-    print("WORST", max(w))
+    if len(sys.argv) > 1 and sys.argv[1] == "--own":
+        kind, N, n, M, gain = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), float(sys.argv[6])
+        print("WORST", run_own(kind, N, n, M, gain))
+    else:
+        names = sys.argv[1:] or ["train_cvrp_n20"]
+        w = [run(n, verbose=False) for n in names]
+        print("WORST", max(w))
