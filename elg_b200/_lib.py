@@ -72,6 +72,7 @@ SYMBOLS = {
                                     _I, _P, _P, _P, _SZ, _P]),
     "elg_adam_step": (_I, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                            C.c_float, _P]),
+    "elg_generate_problems": (_I, [_I, _I, _I, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, _U64, _P, _P, _P, _P]),
     "elg_selftest_umma": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

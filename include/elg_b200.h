@@ -240,6 +240,15 @@ int elg_reinforce_backward(const elg_model_desc* desc, const float* weights, con
 int elg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step,
                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
+/* ---- training-data generators ------------------------------------------------------------------
+ * generate_vrp_data (CVRP/generate_data.py:9-92) / generate_tsp_data (TSP/generate_data.py:9-57) on the device.
+ *   kind: 0 uniform, 1 cluster, 2 mixed (config.yml distribution.data_type); n_cluster = distribution.n_cluster
+ *   (cluster) or n_cluster_mix (mixed); lower / upper / std as in config.yml; capacity = CAPACITIES[problem_size].
+ * Outputs: depot_xy [n][2] and node_demand [n][n_nodes] (cvrp; NULL for tsp), node_xy [n][n_nodes][2].
+ * Counter-based Philox streams keyed by (seed, instance): same distributions as the reference, not its bit stream. */
+int elg_generate_problems(int problem, int kind, int n, int n_nodes, int n_cluster, float lower, float upper, float std,
+                          float capacity, uint64_t seed, float* depot_xy, float* node_xy, float* node_demand, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------------------------
  * One split-precision tcgen05 GEMM  D[128][n] = A[rows_a][k] * B[n][k]^T  (fp16 hi/lo operands, fp32
  * accumulation in TMEM; terms = 1: hi*hi only, 3: + hi*lo + lo*hi; alias: 64-row A operand whose upper
