@@ -58,12 +58,10 @@ struct DecodeBwdArgs {
   // materialised per row-step (row = (b * nT + (t - t0)) * M + m)
   float* add;                 // [rows][NP]      penalty + local score per node
   float* dx;                  // [rows][NP]      d loss / d pre-tanh score
-  float* q;                   // [rows][E]
-  float* o;                   // [rows][E]
-  float* dout;                // [rows][E]       d loss / d attention output
-  float* w;                   // [rows][H][NP]   softmax weights
-  float* ds;                  // [rows][H][NP]   d loss / d log2-domain attention score
+  float* o;                   // [rows][E]       attention output (d E' = DX^T O)
   // accumulators
+  float* dV;                  // [B][N1][E]
+  float* dK;                  // [B][N1][E]  (w.r.t. K' = K log2(e)/sqrt(D))
   float* dqtab;               // [B][N1][E]
   float* dqfirst;             // [B][N1][E] (tsp)
   float* dwl;                 // [E]  d load column of Wq_last (cvrp)

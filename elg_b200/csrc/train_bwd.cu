@@ -401,7 +401,7 @@ static TrainWs train_ws(const elg_model_desc* d, int B, int M, int N1, int t_max
   w.total = o;
   return w;
 }
-static inline long long chunk_row_floats(int NP) { return 3LL * E + 2LL * NP + 2LL * H * NP; }
+static inline long long chunk_row_floats(int NP) { return (long long)E + 2LL * NP; }
 
 }  // namespace elg
 
@@ -446,7 +446,7 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
   const float* sv = reinterpret_cast<const float*>(saved);
   const long long avail = (long long)(workspace_bytes / sizeof(float)) - w.chunk - 64;
   int nT = (int)(avail / ((long long)B * M * chunk_row_floats(NP)));
-  if (nT > 32) nT = 32;
+  if (nT > 64) nT = 64;
   if (nT > T) nT = T;
   ELG_REQUIRE(nT >= 1, ELG_ENOMEM, "workspace too small for one step");
 
@@ -472,15 +472,12 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
   a.problem = d->problem; a.B = B; a.M = M; a.N1 = N1; a.NP = NP; a.k_local = d->local_k; a.flags = d->flags;
   a.xi = d->xi; a.clip = d->clip; a.rec = rec; a.T = T; a.coef = coef;
   a.dqtab = ws + w.dqtab; a.dqfirst = cvrp ? nullptr : ws + w.dqfirst; a.dwl = ws + w.dwl; a.lg = ws + w.lg;
+  a.dV = ws + w.dV; a.dK = ws + w.dK;
   const long long crow = (long long)B * nT * M;
   float* cb = ws + w.chunk;
   a.add = cb; cb += crow * NP;
   a.dx = cb; cb += crow * NP;
-  a.q = cb; cb += crow * E;
-  a.o = cb; cb += crow * E;
-  a.dout = cb; cb += crow * E;
-  a.w = cb; cb += crow * H * NP;
-  a.ds = cb;
+  a.o = cb;
   for (int t0 = cvrp ? 2 : 1; t0 < T; t0 += nT) {
     a.t0 = t0;
     a.nT = (T - t0) < nT ? (T - t0) : nT;
@@ -498,16 +495,6 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
     // d eb[b] += DX[b]^T 1
     p.B = nullptr; p.sBk = 0; p.sBn = 1; p.bB1 = 0; p.C = ws + w.deb; p.ldc = 1; p.bC1 = N1; p.N = 1;
     ELG_TRY(launch_gemm(p, st));
-    // d V[b][:, head] += W[b, head]^T DO[b][:, head];  d K'[b][:, head] += DS[b, head]^T Q[b][:, head]
-    GemmP g;
-    g.sAm = 1; g.sAk = (long long)H * NP; g.bA1 = (long long)Rb * H * NP; g.bA2 = NP;
-    g.sBk = E; g.sBn = 1; g.bB1 = (long long)Rb * E; g.bB2 = D;
-    g.ldc = E; g.bC1 = (long long)N1 * E; g.bC2 = D;
-    g.M = N1; g.N = D; g.K = Rb; g.nb1 = B; g.nb2 = H; g.accumulate = 1;
-    g.A = a.w; g.B = a.dout; g.C = ws + w.dV;
-    ELG_TRY(launch_gemm(g, st));
-    g.A = a.ds; g.B = a.q; g.C = ws + w.dK;
-    ELG_TRY(launch_gemm(g, st));
   }
   ELG_TRY(launch_local_fold_bwd(d, L, weights, derived, ws + w.lg, grads, st));
 

@@ -8,7 +8,8 @@
 // per-row-step vectors to HBM, and batched GEMMs (train_bwd.cu) that contract them over the rows of an instance:
 //   replay_kernel        tours -> per (instance, step, row) state {cur, load, mask bits, action}
 //   local_kernel<FWD>    penalty + local-policy score per node            -> ADD[row][node]
-//   global_bwd_kernel    q, attention, score, softmax; d logits -> DX, DO, DS and the query-table gradient
+//   global_bwd_kernel    q, attention, score, softmax; d logits -> DX, O (for d E'), and in registers d V, d K';
+//                        query-table gradient by atomics
 //   local_kernel<BWD>    gradient of the local policy (register accumulators, flushed once per warp)
 //   local_fold_bwd       chain rule through the constant-query folds -> gradients of the local policy's parameters
 #include "train.cuh"
@@ -419,6 +420,12 @@ __device__ __forceinline__ float dot16(const float* __restrict__ a, const float*
   return s;
 }
 
+constexpr int GTS = 4;         // rollout steps per CTA (tables staged once, accumulators flushed once)
+constexpr int GNJ = 14;        // nodes per warp in the accumulation phases (8 warps x 14 >= 112)
+
+// Per 8-row batch: phase 1a (warp = row) query, attention weights, attention output, scores, softmax, d logits, d o;
+// phase 2a (warp = node slice, lane = 4 channels) d V += w^T d o over the batch's rows; phase 1b softmax backward
+// (d s overwrites w) and d q; phase 2b d K' += d s^T q.  d V and d K' live in registers for the whole CTA.
 template <bool CVRP>
 __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   extern __shared__ __align__(16) float gsm[];
@@ -429,36 +436,16 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   float* seb = sE + N1 * GS;            // [128]
   float* swl = seb + 128;               // [128]
   float* pw = swl + 128;                // per warp: sq[128] so[128] sdo[128] sdx[128] sw[H][WS]
+  __shared__ int sact[GW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / A.nT, tl = blockIdx.x % A.nT;
+  const int nTB = (A.nT + GTS - 1) / GTS;
+  const int b = blockIdx.x / nTB, tb = blockIdx.x % nTB;
   constexpr int PWF = 4 * 128 + H * WS;
   float* sq = pw + warp * PWF;
   float* so = sq + 128;
   float* sdo = so + 128;
   float* sdx = sdo + 128;
   float* sw = sdx + 128;
-
-  // any active row in this (instance, step)?  (uniform over the CTA)
-  const StepRec* recs = A.rec + ((size_t)b * A.T + A.t0 + tl) * M;
-  int any = 0;
-  for (int m = tid; m < M; m += GW * 32) any |= recs[m].active;
-  any = __syncthreads_or(any);
-  const size_t row0 = ((size_t)b * A.nT + tl) * M;
-  if (!any) {
-    // the batched GEMMs read every row of the chunk: zero this CTA's rows
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (size_t i = tid; i < (size_t)M * E / 4; i += GW * 32) {
-      reinterpret_cast<float4*>(A.q + row0 * E)[i] = z4;
-      reinterpret_cast<float4*>(A.o + row0 * E)[i] = z4;
-      reinterpret_cast<float4*>(A.dout + row0 * E)[i] = z4;
-    }
-    for (size_t i = tid; i < (size_t)M * NP / 4; i += GW * 32) reinterpret_cast<float4*>(A.dx + row0 * NP)[i] = z4;
-    for (size_t i = tid; i < (size_t)M * H * NP / 4; i += GW * 32) {
-      reinterpret_cast<float4*>(A.w + row0 * H * NP)[i] = z4;
-      reinterpret_cast<float4*>(A.ds + row0 * H * NP)[i] = z4;
-    }
-    return;
-  }
   {
     const float* gk = A.t.k + (size_t)b * N1 * E;
     const float* gv = A.t.v + (size_t)b * N1 * E;
@@ -477,175 +464,225 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   __syncthreads();
   const int c4 = lane * 4, hl = lane >> 2;
   float4 dwl_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 accV[GNJ], accK[GNJ];
+#pragma unroll
+  for (int i = 0; i < GNJ; ++i) accV[i] = accK[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float ln2 = 0.6931471805599453f;
-  for (int m = warp; m < M; m += GW) {
-    const size_t row = row0 + m;
-    const StepRec rc = recs[m];
-    float* gq = A.q + row * E;
-    float* go = A.o + row * E;
-    float* gdo = A.dout + row * E;
-    float* gdx = A.dx + row * NP;
-    float* gw = A.w + row * H * NP;
-    float* gds = A.ds + row * H * NP;
-    if (!rc.active) {
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(gq + c4) = z4;
-      *reinterpret_cast<float4*>(go + c4) = z4;
-      *reinterpret_cast<float4*>(gdo + c4) = z4;
-      for (int j = lane; j < NP; j += 32) gdx[j] = 0.f;
-      for (int j = lane; j < H * NP; j += 32) { gw[j] = 0.f; gds[j] = 0.f; }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int tl_end = min(A.nT, tb * GTS + GTS);
+  for (int tl = tb * GTS; tl < tl_end; ++tl) {
+    const StepRec* recs = A.rec + ((size_t)b * A.T + A.t0 + tl) * M;
+    const size_t row0 = ((size_t)b * A.nT + tl) * M;
+    int any = 0;
+    for (int m = tid; m < M; m += GW * 32) any |= recs[m].active;
+    any = __syncthreads_or(any);
+    if (!any) {      // the batched GEMM reads every row of the chunk: zero this step's rows
+      for (size_t i = tid; i < (size_t)M * E / 4; i += GW * 32) reinterpret_cast<float4*>(A.o + row0 * E)[i] = z4;
+      for (size_t i = tid; i < (size_t)M * NP / 4; i += GW * 32) reinterpret_cast<float4*>(A.dx + row0 * NP)[i] = z4;
       continue;
     }
-    const int cur = rc.cur;
-    const float load = CVRP ? rc.load : 0.f;
-    const int first = CVRP ? 0 : __float_as_int(rc.load);
-    // ---- query (CVRP/models.py:336-340: Wq_last [enc[cur]; load]; TSP/models.py:258-260: q_first + Wq_last enc[cur])
-    float4 q4 = *reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + c4);
-    if (CVRP) {
-      const float4 wl4 = *reinterpret_cast<const float4*>(swl + c4);
-      q4.x = fmaf(load, wl4.x, q4.x); q4.y = fmaf(load, wl4.y, q4.y); q4.z = fmaf(load, wl4.z, q4.z); q4.w = fmaf(load, wl4.w, q4.w);
-    } else {
-      const float4 f4 = *reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + first) * E + c4);
-      q4.x += f4.x; q4.y += f4.y; q4.z += f4.z; q4.w += f4.w;
-    }
-    __syncwarp();
-    *reinterpret_cast<float4*>(sq + c4) = q4;
-    *reinterpret_cast<float4*>(gq + c4) = q4;
-    __syncwarp();
-    // ---- multi-head attention weights (log2 domain: K' carries log2(e)/sqrt(D))
-#pragma unroll 1
-    for (int h = 0; h < H; ++h) {
-      float sc[4];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = lane + 32 * i;
-        float s = -INFINITY;
-        if (j < N1 && !((rc.mask[i] >> lane) & 1u)) s = dot16(sq + h * D, sK + j * GS + h * D);
-        sc[i] = s;
-        mx = fmaxf(mx, s);
+    for (int m0 = 0; m0 < M; m0 += GW) {
+      const int m = m0 + warp;
+      const bool valid = m < M;
+      StepRec rc;
+      rc.active = 0;
+      if (valid) rc = recs[m];
+      const bool act = valid && rc.active;
+      if (lane == 0) sact[warp] = act ? 1 : 0;
+      const size_t row = row0 + m;
+      float* go = A.o + row * E;
+      float* gdx = A.dx + row * NP;
+      const int cur = rc.cur;
+      const float load = CVRP ? rc.load : 0.f;
+      const int first = CVRP ? 0 : __float_as_int(rc.load);
+      if (valid && !act) {
+        *reinterpret_cast<float4*>(go + c4) = z4;
+        for (int j = lane; j < NP; j += 32) gdx[j] = 0.f;
       }
-      mx = warp_max(mx);
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { sc[i] = exp2f(sc[i] - mx); sum += sc[i]; }
-      sum = warp_sum(sum);
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = lane + 32 * i;
-        if (j < NP) {
-          const float wv = j < N1 ? sc[i] * inv : 0.f;
-          if (j < N1) sw[h * WS + j] = wv;
-          gw[h * NP + j] = wv;
+      if (act) {
+        // ---- query (CVRP/models.py:336-340: Wq_last [enc[cur]; load]; TSP/models.py:258-260: q_first + Wq_last enc[cur])
+        float4 q4 = *reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + c4);
+        if (CVRP) {
+          const float4 wl4 = *reinterpret_cast<const float4*>(swl + c4);
+          q4.x = fmaf(load, wl4.x, q4.x); q4.y = fmaf(load, wl4.y, q4.y); q4.z = fmaf(load, wl4.z, q4.z); q4.w = fmaf(load, wl4.w, q4.w);
+        } else {
+          const float4 f4 = *reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + first) * E + c4);
+          q4.x += f4.x; q4.y += f4.y; q4.z += f4.z; q4.w += f4.w;
         }
-      }
-    }
-    __syncwarp();
-    // ---- attention output o[c], lane = 4 channels of head hl
-    float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < N1; ++j) {
-      const float wv = sw[hl * WS + j];
-      const float4 v4 = *reinterpret_cast<const float4*>(sV + j * GS + c4);
-      o4.x = fmaf(wv, v4.x, o4.x); o4.y = fmaf(wv, v4.y, o4.y); o4.z = fmaf(wv, v4.z, o4.z); o4.w = fmaf(wv, v4.w, o4.w);
-    }
-    *reinterpret_cast<float4*>(so + c4) = o4;
-    *reinterpret_cast<float4*>(go + c4) = o4;
-    __syncwarp();
-    // ---- scores, clipping, softmax over the nodes, d logits
-    float xs[4], th[4], lg[4];
-    float mx = -INFINITY;
-    const float* addr = A.add + row * NP;
+        *reinterpret_cast<float4*>(sq + c4) = q4;
+        __syncwarp();
+        // ---- multi-head attention weights (log2 domain: K' carries log2(e)/sqrt(D))
+#pragma unroll 1
+        for (int h = 0; h < H; ++h) {
+          float sc[4];
+          float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = lane + 32 * i;
-      lg[i] = -INFINITY; th[i] = 0.f; xs[i] = 0.f;
-      if (j < N1 && !((rc.mask[i] >> lane) & 1u)) {
-        float s = seb[j];
-        const float* er = sE + j * GS;
+          for (int i = 0; i < 4; ++i) {
+            const int j = lane + 32 * i;
+            float s = -INFINITY;
+            if (j < N1 && !((rc.mask[i] >> lane) & 1u)) s = dot16(sq + h * D, sK + j * GS + h * D);
+            sc[i] = s;
+            mx = fmaxf(mx, s);
+          }
+          mx = warp_max(mx);
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { sc[i] = exp2f(sc[i] - mx); sum += sc[i]; }
+          sum = warp_sum(sum);
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = lane + 32 * i;
+            if (j < N1) sw[h * WS + j] = sc[i] * inv;
+          }
+        }
+        __syncwarp();
+        // ---- attention output o[c], lane = 4 channels of head hl
+        float4 o4 = z4;
+        for (int j = 0; j < N1; ++j) {
+          const float wv = sw[hl * WS + j];
+          const float4 v4 = *reinterpret_cast<const float4*>(sV + j * GS + c4);
+          o4.x = fmaf(wv, v4.x, o4.x); o4.y = fmaf(wv, v4.y, o4.y); o4.z = fmaf(wv, v4.z, o4.z); o4.w = fmaf(wv, v4.w, o4.w);
+        }
+        *reinterpret_cast<float4*>(so + c4) = o4;
+        *reinterpret_cast<float4*>(go + c4) = o4;
+        __syncwarp();
+        // ---- scores, clipping, softmax over the nodes, d logits
+        float th[4], lg[4];
+        float mx = -INFINITY;
+        const float* addr = A.add + row * NP;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = lane + 32 * i;
+          lg[i] = -INFINITY; th[i] = 0.f;
+          if (j < N1 && !((rc.mask[i] >> lane) & 1u)) {
+            float s = seb[j];
+            const float* er = sE + j * GS;
 #pragma unroll 8
-        for (int c = 0; c < E; c += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(so + c);
-          const float4 e4 = *reinterpret_cast<const float4*>(er + c);
-          s = fmaf(a.x, e4.x, s); s = fmaf(a.y, e4.y, s); s = fmaf(a.z, e4.z, s); s = fmaf(a.w, e4.w, s);
+            for (int c = 0; c < E; c += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(so + c);
+              const float4 e4 = *reinterpret_cast<const float4*>(er + c);
+              s = fmaf(a.x, e4.x, s); s = fmaf(a.y, e4.y, s); s = fmaf(a.z, e4.z, s); s = fmaf(a.w, e4.w, s);
+            }
+            th[i] = tanhf(s + addr[j]);
+            lg[i] = A.clip * th[i];
+          }
+          mx = fmaxf(mx, lg[i]);
         }
-        xs[i] = s + addr[j];
-        th[i] = tanhf(xs[i]);
-        lg[i] = A.clip * th[i];
-      }
-      mx = fmaxf(mx, lg[i]);
-    }
-    mx = warp_max(mx);
-    float pe[4], sum = 0.f;
+        mx = warp_max(mx);
+        float pe[4], sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { pe[i] = __expf(lg[i] - mx); sum += pe[i]; }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    const float cf = A.coef[(size_t)b * M + m];
+        for (int i = 0; i < 4; ++i) { pe[i] = __expf(lg[i] - mx); sum += pe[i]; }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        const float cf = A.coef[(size_t)b * M + m];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = lane + 32 * i;
-      float dxv = 0.f;
-      if (lg[i] != -INFINITY) {
-        const float dl = cf * ((j == rc.act ? 1.f : 0.f) - pe[i] * inv);
-        dxv = dl * A.clip * (1.f - th[i] * th[i]);
+        for (int i = 0; i < 4; ++i) {
+          const int j = lane + 32 * i;
+          float dxv = 0.f;
+          if (lg[i] != -INFINITY) {
+            const float dl = cf * ((j == rc.act ? 1.f : 0.f) - pe[i] * inv);
+            dxv = dl * A.clip * (1.f - th[i] * th[i]);
+          }
+          sdx[j] = dxv;
+          if (j < NP) gdx[j] = dxv;
+        }
+        __syncwarp();
+        // ---- d o = sum_j dx_j E'_j
+        float4 d4 = z4;
+        for (int j = 0; j < N1; ++j) {
+          const float x = sdx[j];
+          const float4 e4 = *reinterpret_cast<const float4*>(sE + j * GS + c4);
+          d4.x = fmaf(x, e4.x, d4.x); d4.y = fmaf(x, e4.y, d4.y); d4.z = fmaf(x, e4.z, d4.z); d4.w = fmaf(x, e4.w, d4.w);
+        }
+        *reinterpret_cast<float4*>(sdo + c4) = d4;
       }
-      if (j < 128) sdx[j] = dxv;
-      if (j < NP) gdx[j] = dxv;
-    }
-    __syncwarp();
-    // ---- d o = sum_j dx_j E'_j
-    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < N1; ++j) {
-      const float x = sdx[j];
-      const float4 e4 = *reinterpret_cast<const float4*>(sE + j * GS + c4);
-      d4.x = fmaf(x, e4.x, d4.x); d4.y = fmaf(x, e4.y, d4.y); d4.z = fmaf(x, e4.z, d4.z); d4.w = fmaf(x, e4.w, d4.w);
-    }
-    *reinterpret_cast<float4*>(sdo + c4) = d4;
-    *reinterpret_cast<float4*>(gdo + c4) = d4;
-    __syncwarp();
-    // ---- softmax backward per head: d s2_hj = ln2 * w_hj (d w_hj - sum_j w d w)
+      __syncthreads();
+      // ---- phase 2a: d V[j][c] += w_r[h(c)][j] d o_r[c] over the rows of the batch (warp = nodes warp, warp+8, ...)
 #pragma unroll 1
-    for (int h = 0; h < H; ++h) {
-      float dw[4], wv[4];
-      float part = 0.f;
+      for (int r = 0; r < GW; ++r) {
+        if (!sact[r]) continue;
+        const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
+        const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + 2 * 128 + c4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = lane + 32 * i;
-        dw[i] = 0.f; wv[i] = 0.f;
-        if (j < N1) {
-          wv[i] = sw[h * WS + j];
-          dw[i] = dot16(sdo + h * D, sV + j * GS + h * D);
-        }
-        part = fmaf(wv[i], dw[i], part);
-      }
-      const float wbar = warp_sum(part);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = lane + 32 * i;
-        if (j < NP) {
-          const float d = j < N1 ? ln2 * wv[i] * (dw[i] - wbar) : 0.f;
-          if (j < N1) sw[h * WS + j] = d;
-          gds[h * NP + j] = d;
+        for (int i = 0; i < GNJ; ++i) {
+          const int j = warp + GW * i;
+          const float wv = j < N1 ? rw[j] : 0.f;
+          accV[i].x = fmaf(wv, g4.x, accV[i].x); accV[i].y = fmaf(wv, g4.y, accV[i].y);
+          accV[i].z = fmaf(wv, g4.z, accV[i].z); accV[i].w = fmaf(wv, g4.w, accV[i].w);
         }
       }
+      __syncthreads();
+      if (act) {
+        // ---- softmax backward per head: d s2_hj = ln2 * w_hj (d w_hj - sum_j w d w), in place over w
+#pragma unroll 1
+        for (int h = 0; h < H; ++h) {
+          float dw[4], wv[4];
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = lane + 32 * i;
+            dw[i] = 0.f; wv[i] = 0.f;
+            if (j < N1) {
+              wv[i] = sw[h * WS + j];
+              dw[i] = dot16(sdo + h * D, sV + j * GS + h * D);
+            }
+            part = fmaf(wv[i], dw[i], part);
+          }
+          const float wbar = warp_sum(part);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = lane + 32 * i;
+            if (j < N1) sw[h * WS + j] = ln2 * wv[i] * (dw[i] - wbar);
+          }
+        }
+        __syncwarp();
+        // ---- d q = sum_j d s2_hj K'_j ; scatter into the query-table gradient
+        float4 g4 = z4;
+        for (int j = 0; j < N1; ++j) {
+          const float x = sw[hl * WS + j];
+          const float4 k4 = *reinterpret_cast<const float4*>(sK + j * GS + c4);
+          g4.x = fmaf(x, k4.x, g4.x); g4.y = fmaf(x, k4.y, g4.y); g4.z = fmaf(x, k4.z, g4.z); g4.w = fmaf(x, k4.w, g4.w);
+        }
+        float* dq = A.dqtab + ((size_t)b * N1 + cur) * E + c4;
+        atomicAdd(dq + 0, g4.x); atomicAdd(dq + 1, g4.y); atomicAdd(dq + 2, g4.z); atomicAdd(dq + 3, g4.w);
+        if (CVRP) {
+          dwl_acc.x = fmaf(load, g4.x, dwl_acc.x); dwl_acc.y = fmaf(load, g4.y, dwl_acc.y);
+          dwl_acc.z = fmaf(load, g4.z, dwl_acc.z); dwl_acc.w = fmaf(load, g4.w, dwl_acc.w);
+        } else {
+          float* df = A.dqfirst + ((size_t)b * N1 + first) * E + c4;
+          atomicAdd(df + 0, g4.x); atomicAdd(df + 1, g4.y); atomicAdd(df + 2, g4.z); atomicAdd(df + 3, g4.w);
+        }
+      }
+      __syncthreads();
+      // ---- phase 2b: d K'[j][c] += d s_r[h(c)][j] q_r[c]
+#pragma unroll 1
+      for (int r = 0; r < GW; ++r) {
+        if (!sact[r]) continue;
+        const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
+        const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + c4);
+#pragma unroll
+        for (int i = 0; i < GNJ; ++i) {
+          const int j = warp + GW * i;
+          const float wv = j < N1 ? rw[j] : 0.f;
+          accK[i].x = fmaf(wv, g4.x, accK[i].x); accK[i].y = fmaf(wv, g4.y, accK[i].y);
+          accK[i].z = fmaf(wv, g4.z, accK[i].z); accK[i].w = fmaf(wv, g4.w, accK[i].w);
+        }
+      }
+      __syncthreads();
     }
-    __syncwarp();
-    // ---- d q = sum_j d s2_hj K'_j ; scatter into the query-table gradient
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < N1; ++j) {
-      const float x = sw[hl * WS + j];
-      const float4 k4 = *reinterpret_cast<const float4*>(sK + j * GS + c4);
-      g4.x = fmaf(x, k4.x, g4.x); g4.y = fmaf(x, k4.y, g4.y); g4.z = fmaf(x, k4.z, g4.z); g4.w = fmaf(x, k4.w, g4.w);
-    }
-    float* dq = A.dqtab + ((size_t)b * N1 + cur) * E + c4;
-    atomicAdd(dq + 0, g4.x); atomicAdd(dq + 1, g4.y); atomicAdd(dq + 2, g4.z); atomicAdd(dq + 3, g4.w);
-    if (CVRP) {
-      dwl_acc.x = fmaf(load, g4.x, dwl_acc.x); dwl_acc.y = fmaf(load, g4.y, dwl_acc.y);
-      dwl_acc.z = fmaf(load, g4.z, dwl_acc.z); dwl_acc.w = fmaf(load, g4.w, dwl_acc.w);
-    } else {
-      float* df = A.dqfirst + ((size_t)b * N1 + first) * E + c4;
-      atomicAdd(df + 0, g4.x); atomicAdd(df + 1, g4.y); atomicAdd(df + 2, g4.z); atomicAdd(df + 3, g4.w);
+  }
+  // ---- flush
+  float* gV = A.dV + (size_t)b * N1 * E;
+  float* gK = A.dK + (size_t)b * N1 * E;
+#pragma unroll
+  for (int i = 0; i < GNJ; ++i) {
+    const int j = warp + GW * i;
+    if (j < N1) {
+      float* pv = gV + j * E + c4;
+      float* pk = gK + j * E + c4;
+      atomicAdd(pv + 0, accV[i].x); atomicAdd(pv + 1, accV[i].y); atomicAdd(pv + 2, accV[i].z); atomicAdd(pv + 3, accV[i].w);
+      atomicAdd(pk + 0, accK[i].x); atomicAdd(pk + 1, accK[i].y); atomicAdd(pk + 2, accK[i].z); atomicAdd(pk + 3, accK[i].w);
     }
   }
   if (CVRP) {
@@ -656,10 +693,10 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
 
 int launch_global_bwd(const DecodeBwdArgs& a, cudaStream_t st) {
   const size_t smem = ((size_t)3 * a.N1 * GS + 256 + (size_t)GW * (4 * 128 + H * WS)) * sizeof(float);
-  ELG_REQUIRE(smem <= 227 * 1024, ELG_EUNSUPPORTED, "training supports up to %d nodes (needs %zu bytes of shared memory)", TRAIN_MAX_NODES, smem);
+  ELG_REQUIRE(smem <= 226 * 1024, ELG_EUNSUPPORTED, "training supports up to %d nodes (needs %zu bytes of shared memory)", TRAIN_MAX_NODES, smem);
   ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)(a.B * a.nT);
+  const unsigned grid = (unsigned)(a.B * ((a.nT + GTS - 1) / GTS));
   if (a.problem == ELG_CVRP) global_bwd_kernel<true><<<grid, GW * 32, smem, st>>>(a);
   else global_bwd_kernel<false><<<grid, GW * 32, smem, st>>>(a);
   ELG_LAUNCH_OK();
