@@ -62,6 +62,7 @@ struct DecodeBwdArgs {
   // accumulators
   float* dV;                  // [B][N1][E]
   float* dK;                  // [B][N1][E]  (w.r.t. K' = K log2(e)/sqrt(D))
+  float* deb;                 // [B][N1]
   float* dqtab;               // [B][N1][E]
   float* dqfirst;             // [B][N1][E] (tsp)
   float* dwl;                 // [E]  d load column of Wq_last (cvrp)

@@ -472,7 +472,7 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
   a.problem = d->problem; a.B = B; a.M = M; a.N1 = N1; a.NP = NP; a.k_local = d->local_k; a.flags = d->flags;
   a.xi = d->xi; a.clip = d->clip; a.rec = rec; a.T = T; a.coef = coef;
   a.dqtab = ws + w.dqtab; a.dqfirst = cvrp ? nullptr : ws + w.dqfirst; a.dwl = ws + w.dwl; a.lg = ws + w.lg;
-  a.dV = ws + w.dV; a.dK = ws + w.dK;
+  a.dV = ws + w.dV; a.dK = ws + w.dK; a.deb = ws + w.deb;
   const long long crow = (long long)B * nT * M;
   float* cb = ws + w.chunk;
   a.add = cb; cb += crow * NP;
@@ -491,9 +491,6 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
     p.B = a.o; p.sBk = E; p.sBn = 1; p.bB1 = (long long)Rb * E;
     p.C = ws + w.dEp; p.ldc = E; p.bC1 = (long long)N1 * E;
     p.M = N1; p.N = E; p.K = Rb; p.nb1 = B; p.nb2 = 1; p.accumulate = 1;
-    ELG_TRY(launch_gemm(p, st));
-    // d eb[b] += DX[b]^T 1
-    p.B = nullptr; p.sBk = 0; p.sBn = 1; p.bB1 = 0; p.C = ws + w.deb; p.ldc = 1; p.bC1 = N1; p.N = 1;
     ELG_TRY(launch_gemm(p, st));
   }
   ELG_TRY(launch_local_fold_bwd(d, L, weights, derived, ws + w.lg, grads, st));

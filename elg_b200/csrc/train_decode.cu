@@ -405,7 +405,6 @@ int launch_local(const DecodeBwdArgs& a, bool bwd, cudaStream_t st) {
 // Global policy: one CTA per (instance, step), K', V, E' of the instance staged in shared memory (row stride 132
 // floats: conflict-free both for "lane = node" row reads and "lane = 4 channels" column sweeps); one warp per row.
 // =================================================================================================================
-constexpr int GW = 8;          // warps per CTA
 constexpr int GS = 132;        // table row stride (floats)
 constexpr int WS = 113;        // stride of the per-head softmax-weight rows (odd: heads land in different banks)
 
@@ -421,13 +420,13 @@ __device__ __forceinline__ float dot16(const float* __restrict__ a, const float*
 }
 
 constexpr int GTS = 4;         // rollout steps per CTA (tables staged once, accumulators flushed once)
-constexpr int GNJ = 14;        // nodes per warp in the accumulation phases (8 warps x 14 >= 112)
 
 // Per 8-row batch: phase 1a (warp = row) query, attention weights, attention output, scores, softmax, d logits, d o;
 // phase 2a (warp = node slice, lane = 4 channels) d V += w^T d o over the batch's rows; phase 1b softmax backward
 // (d s overwrites w) and d q; phase 2b d K' += d s^T q.  d V and d K' live in registers for the whole CTA.
-template <bool CVRP>
+template <bool CVRP, int GW>
 __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
+  constexpr int GNJ = (TRAIN_MAX_NODES + GW - 1) / GW;     // nodes per warp in the accumulation phases
   extern __shared__ __align__(16) float gsm[];
   const int N1 = A.N1, NP = A.NP, M = A.M;
   float* sK = gsm;
@@ -435,7 +434,8 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   float* sE = sV + N1 * GS;
   float* seb = sE + N1 * GS;            // [128]
   float* swl = seb + 128;               // [128]
-  float* pw = swl + 128;                // per warp: sq[128] so[128] sdo[128] sdx[128] sw[H][WS]
+  float* sdeb = swl + 128;              // [128]  d eb of this CTA (shared-memory atomics)
+  float* pw = sdeb + 128;               // per warp: sq[128] so[128] sdo[128] sdx[128] sw[H][WS]
   __shared__ int sact[GW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nTB = (A.nT + GTS - 1) / GTS;
@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
     for (int i = tid; i < 128; i += GW * 32) {
       seb[i] = i < N1 ? A.t.eb[(size_t)b * N1 + i] : 0.f;
       swl[i] = A.derived[DER_WL + i];
+      sdeb[i] = 0.f;
     }
   }
   __syncthreads();
@@ -586,6 +587,7 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
           }
           sdx[j] = dxv;
           if (j < NP) gdx[j] = dxv;
+          if (dxv != 0.f) atomicAdd(sdeb + j, dxv);
         }
         __syncwarp();
         // ---- d o = sum_j dx_j E'_j
@@ -685,22 +687,31 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
       atomicAdd(pk + 0, accK[i].x); atomicAdd(pk + 1, accK[i].y); atomicAdd(pk + 2, accK[i].z); atomicAdd(pk + 3, accK[i].w);
     }
   }
+  __syncthreads();
+  for (int j = tid; j < N1; j += GW * 32) atomicAdd(A.deb + (size_t)b * N1 + j, sdeb[j]);
   if (CVRP) {
     atomicAdd(A.dwl + c4 + 0, dwl_acc.x); atomicAdd(A.dwl + c4 + 1, dwl_acc.y);
     atomicAdd(A.dwl + c4 + 2, dwl_acc.z); atomicAdd(A.dwl + c4 + 3, dwl_acc.w);
   }
 }
 
-int launch_global_bwd(const DecodeBwdArgs& a, cudaStream_t st) {
-  const size_t smem = ((size_t)3 * a.N1 * GS + 256 + (size_t)GW * (4 * 128 + H * WS)) * sizeof(float);
+template <bool CVRP, int GW>
+static int launch_global_bwd_t(const DecodeBwdArgs& a, cudaStream_t st) {
+  const size_t smem = ((size_t)3 * a.N1 * GS + 384 + (size_t)GW * (4 * 128 + H * WS)) * sizeof(float);
   ELG_REQUIRE(smem <= 226 * 1024, ELG_EUNSUPPORTED, "training supports up to %d nodes (needs %zu bytes of shared memory)", TRAIN_MAX_NODES, smem);
-  ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<CVRP, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(a.B * ((a.nT + GTS - 1) / GTS));
-  if (a.problem == ELG_CVRP) global_bwd_kernel<true><<<grid, GW * 32, smem, st>>>(a);
-  else global_bwd_kernel<false><<<grid, GW * 32, smem, st>>>(a);
+  global_bwd_kernel<CVRP, GW><<<grid, GW * 32, smem, st>>>(a);
   ELG_LAUNCH_OK();
   return ELG_OK;
+}
+
+// 12 warps per CTA when the instance tables leave room for their scratch (N1 <= 101), else 8
+int launch_global_bwd(const DecodeBwdArgs& a, cudaStream_t st) {
+  const size_t smem12 = ((size_t)3 * a.N1 * GS + 384 + (size_t)12 * (4 * 128 + H * WS)) * sizeof(float);
+  const bool wide = smem12 <= 226 * 1024;
+  if (a.problem == ELG_CVRP) return wide ? launch_global_bwd_t<true, 12>(a, st) : launch_global_bwd_t<true, 8>(a, st);
+  return wide ? launch_global_bwd_t<false, 12>(a, st) : launch_global_bwd_t<false, 8>(a, st);
 }
 
 // =================================================================================================================
