@@ -10,7 +10,8 @@
 namespace elg {
 
 // ---------------------------------------------------------------------------------------------------------------
-// Generic strided / batched SGEMM (fp32 FMA), BK = 16, 256 threads, (BM/TM) x (BN/TN) thread grid.
+// Generic strided / batched SGEMM (fp32 FMA), BK = 16, 256 threads, (BM/TM) x (BN/TN) thread grid, register-prefetched
+// k-tiles (the next tile's global loads overlap the current tile's arithmetic).
 // ---------------------------------------------------------------------------------------------------------------
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
@@ -37,20 +38,44 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   const bool a_kfast = p.sAk == 1;
   const bool b_nfast = p.sBn == 1;
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    for (int e = tid; e < BM * BK; e += 256) {
+  constexpr int NA = BM * BK / 256, NB = (BN * BK + 255) / 256;
+  float ra[NA], rb[NB];
+  // global -> registers for the k-tile starting at k0 (zero outside the matrix / this split's k-range)
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+      const int e = tid + u * 256;
       int m, k;
       if (a_kfast) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < p.M && gk < kend) ? A[gm * p.sAm + gk * p.sAk] : 0.f;
+      ra[u] = (gm < p.M && gk < kend) ? A[gm * p.sAm + gk * p.sAk] : 0.f;
     }
-    for (int e = tid; e < BN * BK; e += 256) {
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int e = tid + u * 256;
       int n, k;
       if (b_nfast) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
       const int gn = n0 + n, gk = k0 + k;
-      Bs[k][n] = (gn < p.N && gk < kend) ? (B ? B[gk * p.sBk + gn * p.sBn] : 1.f) : 0.f;
+      rb[u] = (e < BN * BK && gn < p.N && gk < kend) ? (B ? B[gk * p.sBk + gn * p.sBn] : 1.f) : 0.f;
     }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+      const int e = tid + u * 256;
+      if (a_kfast) As[e % BK][e / BK] = ra[u]; else As[e / BM][e % BM] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int e = tid + u * 256;
+      if (e < BN * BK) { if (b_nfast) Bs[e / BN][e % BN] = rb[u]; else Bs[e % BK][e / BK] = rb[u]; }
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    stage();
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);      // next tile's loads are in flight during this tile's arithmetic
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
