@@ -459,7 +459,7 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
   ELG_REQUIRE(weights && derived && t && saved && tours && reward && grads && workspace, ELG_EINVAL, "NULL pointer");
   ELG_REQUIRE(B > 0 && M > 0 && N1 > 1 && T > 0 && T <= t_max, ELG_EINVAL, "bad sizes");
   ELG_REQUIRE(N1 <= TRAIN_MAX_NODES && elg_rollout_resident(d, N1) == 1, ELG_EUNSUPPORTED,
-              "the training path supports instances of up to %d nodes", TRAIN_MAX_NODES);
+              "the training path supports resident instances only (elg_rollout_resident: up to %d nodes, 108 for cvrp with k = 40)", TRAIN_MAX_NODES);
   ELG_REQUIRE(((size_t)workspace & 255) == 0, ELG_EINVAL, "workspace must be 256-byte aligned");
   ELG_REQUIRE(workspace_bytes >= elg_train_workspace_bytes(d, B, M, N1, t_max, 1), ELG_ENOMEM, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;

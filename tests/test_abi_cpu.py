@@ -78,3 +78,27 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "elg_oracle" not in src, f
+
+
+def test_training_entry_points_validate_arguments_without_a_gpu():
+    """Argument errors are reported as ELG_E* codes before any CUDA call (no compute on the CPU box)."""
+    import ctypes as C
+    from elg_b200 import _lib, engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS
+    lib = _lib.lib
+    desc = engine.make_desc("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]))
+    null = C.c_void_p(0)
+    assert lib.elg_train_saved_bytes(desc, 64, 101) == (6 * (8 * 128 + 512) + 128) * 64 * 101 * 4
+    assert lib.elg_train_workspace_bytes(desc, 64, 100, 101, 204, 32) > lib.elg_train_workspace_bytes(desc, 64, 100, 101, 204, 1) > 0
+    assert lib.elg_train_workspace_bytes(desc, 0, 100, 101, 204, 1) == 0
+    out = (C.c_int64 * 8)()
+    assert lib.elg_train_workspace_layout(desc, 4, 20, 21, 44, out) == 0 and list(out)[:4] == sorted(list(out)[:4]) and out[0] == 0
+    t = _lib.Tables()
+    assert lib.elg_encode_train(desc, null, null, t, 1, 21, null, 0, null) == -1           # ELG_EINVAL
+    assert lib.elg_reinforce_backward(desc, null, null, t, null, 1, 20, 21, null, 44, 40, null, null, 1, null, null, null, 0, null) == -1
+    assert b"NULL" in lib.elg_last_error()
+    assert lib.elg_adam_step(null, null, null, null, 10, 1, 1e-4, 0.9, 0.999, 1e-8, 1e-6, 1.0, null) == -1
+    assert lib.elg_generate_problems(1, 5, 4, 20, 3, 0.2, 0.8, 0.07, 30.0, 1, null, null, null, null) == -1
+    bad = engine.make_desc("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]))
+    bad.emb = 64
+    assert lib.elg_train_saved_bytes(bad, 4, 21) == 0

@@ -127,3 +127,65 @@ def test_training_loop_driver_learns_and_checkpoints(tmp_path):
     m.load_state_dict(ck["model_state_dict"])
     log = json.load(open(str(tmp_path / "log.json")))
     assert len(log["result"]["val_100"]) == 1 and len(log["result"]["val_500"]) == 1
+
+
+def _own_rollout_check(kind, N, n, M, scale_norm=True, gain=1.5, tol=2e-2):
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    from elg_b200.trainer import Trainer
+    from oracle import elg_oracle as O
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    sd = synthetic_state_dict(kind, seed=11, gain=gain)
+    tr = Trainer(kind, mp, sd, "cuda:0", scale_norm=scale_norm)
+    if kind == "cvrp":
+        data = synthetic_cvrp_batch(n, N, seed=17)
+        prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], 1)
+    else:
+        data = synthetic_tsp_batch(n, N, seed=17)
+        prob = O.load_tsp(data, 1)
+    random.seed(6)
+    out = tr.forward_backward(data, M, seed=77)
+    torch.cuda.synchronize()
+    tours = out["tours"][:, :, :out["T"]].long().cpu()
+    J, logp, ref, _ = TH.oracle_grads(kind, mp, sd, prob, M, tours, out["reward"].cpu(), scale_norm)
+    assert float((out["logp"].cpu() - logp).abs().max()) < 5e-3 * max(1.0, float(logp.abs().max()))
+    assert abs(float(out["loss"]) - float(J)) < 5e-3 * max(1.0, abs(float(J)))
+    eo = TH.grad_errors_l2(tr.unpack(out["grads"]), ref)
+    assert max(eo.values()) < tol, sorted(eo.items(), key=lambda kv: -kv[1])[:3]
+
+
+@pytest.mark.parametrize("kind,N", [("cvrp", 107), ("tsp", 112)])
+def test_largest_supported_instance_uses_the_8_warp_variant(kind, N):
+    """The resident limit (elg_rollout_resident): 108 nodes for cvrp (k = 40), 112 for tsp; the tables leave room for 8 warps."""
+    _own_rollout_check(kind, N, 2, 40)
+
+
+def test_tsp100_full_width():
+    _own_rollout_check("tsp", 100, 2, 100)
+
+
+def test_fewer_rows_than_warps_and_single_instance():
+    _own_rollout_check("cvrp", 20, 1, 7)
+
+
+def test_without_advantage_scaling():
+    _own_rollout_check("cvrp", 20, 3, 20, scale_norm=False)
+
+
+def test_tsp_scaling_skipped_when_an_instance_has_zero_max_advantage():
+    """TSP/train.py:114-117: the max-advantage scaling applies only if every instance's maximum advantage is non-zero.
+    M = 1 makes every advantage zero -> unscaled J = 0 and an exactly zero gradient (no NaN)."""
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict, synthetic_tsp_batch
+    from elg_b200.trainer import Trainer
+    tr = Trainer("tsp", dict(DEFAULT_MODEL_PARAMS["tsp"]), synthetic_state_dict("tsp", seed=11, gain=1.0), "cuda:0")
+    out = tr.forward_backward(synthetic_tsp_batch(3, 20, seed=1), 1, start_nodes=[0], seed=5)
+    torch.cuda.synchronize()
+    assert float(out["loss"]) == 0.0 and float(out["grads"].abs().max()) == 0.0
+
+
+def test_training_rejects_instances_beyond_the_resident_limit():
+    from elg_b200._lib import ElgError
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
+    from elg_b200.trainer import Trainer
+    tr = Trainer("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]), synthetic_state_dict("cvrp", seed=11, gain=1.0), "cuda:0")
+    with pytest.raises(ElgError):
+        tr.forward_backward(synthetic_cvrp_batch(1, 150, seed=1), 20, seed=5)
