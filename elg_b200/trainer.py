@@ -76,6 +76,31 @@ class Trainer:
         return {k: f[off:off + int(torch.tensor(self._shapes[k]).prod())].reshape(self._shapes[k]).clone()
                 for k, off in self._slots.items()}
 
+    def _pack(self, d, out):
+        host = out.detach().cpu()
+        for k, off in self._slots.items():
+            v = d[k].detach().to("cpu", torch.float32).reshape(-1)
+            host[off:off + v.numel()] = v
+        out.copy_(host)
+
+    def load_checkpoint(self, ck):
+        """Resume from a dict written by `checkpoint()` (or by the reference: its torch Adam state is per-parameter and is
+        accepted too when it carries 'state' / 'param_groups')."""
+        self._pack(ck["model_state_dict"], self.handle.weights)
+        engine.prepare_model(self.handle)
+        opt = ck.get("optimizer_state_dict") or {}
+        if "exp_avg" in opt:
+            self._pack(opt["exp_avg"], self.exp_avg)
+            self._pack(opt["exp_avg_sq"], self.exp_avg_sq)
+            self.step_count = int(opt.get("step", ck.get("step", 0)))
+        elif "state" in opt and opt["state"]:
+            # torch.optim.Adam.state_dict(): parameters in model.parameters() order = state_dict order of the reference
+            keys = [k for k in ck["model_state_dict"] if k in self._slots]
+            st = opt["state"]
+            self._pack({k: st[i]["exp_avg"] for i, k in enumerate(keys)}, self.exp_avg)
+            self._pack({k: st[i]["exp_avg_sq"] for i, k in enumerate(keys)}, self.exp_avg_sq)
+            self.step_count = int(st[0]["step"])
+
     def checkpoint(self):
         return {"step": self.step_count, "model_state_dict": self.state_dict(),
                 "optimizer_state_dict": {"exp_avg": self.unpack(self.exp_avg), "exp_avg_sq": self.unpack(self.exp_avg_sq),

@@ -189,3 +189,26 @@ def test_training_rejects_instances_beyond_the_resident_limit():
     tr = Trainer("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]), synthetic_state_dict("cvrp", seed=11, gain=1.0), "cuda:0")
     with pytest.raises(ElgError):
         tr.forward_backward(synthetic_cvrp_batch(1, 150, seed=1), 20, seed=5)
+
+
+def test_checkpoint_resume_reproduces_the_next_step():
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
+    from elg_b200.trainer import Trainer
+    mp = dict(DEFAULT_MODEL_PARAMS["cvrp"])
+    sd = synthetic_state_dict("cvrp", seed=3, gain=1.0)
+    perm = list(range(20))
+    a = Trainer("cvrp", mp, sd, "cuda:0")
+    for s in range(2):
+        a.step(synthetic_cvrp_batch(4, 20, seed=30 + s), 20, start_nodes=perm, seed=100 + s)
+    ck = a.checkpoint()
+    b = Trainer("cvrp", mp, sd, "cuda:0")
+    b.load_checkpoint(ck)
+    assert b.step_count == 2 and torch.equal(a.handle.weights, b.handle.weights) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+    oa = a.step(synthetic_cvrp_batch(4, 20, seed=32), 20, start_nodes=perm, seed=102)
+    ob = b.step(synthetic_cvrp_batch(4, 20, seed=32), 20, start_nodes=perm, seed=102)
+    torch.cuda.synchronize()
+    assert torch.equal(oa["tours"], ob["tours"])
+    # gradients are accumulated with floating-point atomics: equal up to summation order
+    assert float((a.handle.weights - b.handle.weights).abs().max()) < 1e-6
+    sd2 = b.state_dict()
+    assert all(sd2[k].shape == sd[k].shape for k in sd2)
