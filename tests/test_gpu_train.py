@@ -208,7 +208,9 @@ def test_checkpoint_resume_reproduces_the_next_step():
     ob = b.step(synthetic_cvrp_batch(4, 20, seed=32), 20, start_nodes=perm, seed=102)
     torch.cuda.synchronize()
     assert torch.equal(oa["tours"], ob["tours"])
-    # gradients are accumulated with floating-point atomics: equal up to summation order
-    assert float((a.handle.weights - b.handle.weights).abs().max()) < 1e-6
+    # gradients are accumulated with floating-point atomics: equal up to summation order; Adam turns the rounding noise of
+    # exactly-zero gradients (biases in front of an instance norm) into +-lr steps, so weights agree to a few lr there
+    assert float((oa["grads"] - ob["grads"]).abs().max()) < 1e-4 * float(oa["grads"].abs().max())
+    assert float((a.handle.weights - b.handle.weights).abs().max()) < 2.5e-4
     sd2 = b.state_dict()
     assert all(sd2[k].shape == sd[k].shape for k in sd2)
