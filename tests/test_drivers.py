@@ -85,3 +85,45 @@ def test_tsplib_driver_matches_reference(tmp_path):
     ref_best = float((-g.reward()).min())
     assert rec["scale"] == 52 and abs(rec["best_cost"] - ref_best) / ref_best < 2e-3
     assert os.path.exists(tmp_path / "out" / "ELG_tsplib.json")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cvrp", "tsp"])
+def test_test_py_loop_matches_oracle_costs(kind, capsys):
+    """CVRP/test.py:14-56 / TSP/test.py:14-56 drop-ins: best-of-POMO and best-of-augmentation costs per instance agree
+    with the oracle's rollout on the same instances and start permutation."""
+    import random
+    import torch
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    from oracle import elg_oracle as O
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    sd = synthetic_state_dict(kind, seed=21, gain=3.0)
+    dev = "cuda:0"
+    if kind == "cvrp":
+        from elg_b200.cvrp import CVRPEnv as Env, CVRPModel as Model
+        from elg_b200.cvrp.test import solve_batch, test
+        data = synthetic_cvrp_batch(4, 20, seed=8)
+        batch = {k: v.to(dev) for k, v in data.items()}
+        prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], 8)
+    else:
+        from elg_b200.tsp import TSPEnv as Env, TSPModel as Model
+        from elg_b200.tsp.test import solve_batch, test
+        data = synthetic_tsp_batch(4, 20, seed=8)
+        batch = data.to(dev)
+        prob = O.load_tsp(data, 8)
+    model = Model(**mp)
+    model.decoder.add_local_policy(dev)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    env = Env(20, dev)
+    random.seed(5)
+    no_aug, aug, sol, rew = solve_batch(model, env, batch, 8)
+    perm = O.start_permutation(kind, 20, 20, seed=5)
+    _, _, ref_r = O.rollout(O.Weights(sd, kind, mp), prob, 20, perm, "greedy")
+    ref_no_aug, ref_aug = O.best_of(ref_r, 8, 4)
+    assert float((aug.cpu() - ref_aug).abs().max()) < 1e-4 * float(ref_aug.max())
+    assert float((no_aug.cpu() - ref_no_aug).abs().max()) < 1e-4 * float(ref_no_aug.max())
+    random.seed(5)
+    avg = test([batch], model, env, 8)
+    assert abs(float(avg) - float(ref_aug.mean())) < 1e-4 * float(ref_aug.mean())
+    assert "Aug cost" in capsys.readouterr().out
