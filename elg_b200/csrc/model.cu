@@ -30,8 +30,8 @@ int check_desc(const elg_model_desc* d) {
   ELG_REQUIRE(d->ff > 0 && d->ff % 128 == 0, ELG_EUNSUPPORTED, "ff_hidden_dim must be a positive multiple of 128");
   int kt = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
   ELG_REQUIRE(d->local_k >= 1 && kt <= KT_MAX, ELG_EUNSUPPORTED, "local_size %d outside [1,%d]", d->local_k, KT_MAX - 1);
-  ELG_REQUIRE((d->flags & ELG_FLAG_ENSEMBLE) && (d->flags & ELG_FLAG_DISTANCE_PENALTY), ELG_EUNSUPPORTED,
-              "only the released configuration (ensemble=True, distance_penalty=True) is implemented");
+  ELG_REQUIRE(d->flags & ELG_FLAG_DISTANCE_PENALTY, ELG_EUNSUPPORTED,
+              "distance_penalty=False is not implemented (ensemble may be on or off)");
   return ELG_OK;
 }
 
@@ -223,6 +223,10 @@ int elg_prepare_model(const elg_model_desc* d, const float* weights, float* deri
   cudaStream_t st = (cudaStream_t)stream;
   prepare_kernel<<<1, 256, 0, st>>>(*d, L, weights, derived);
   ELG_LAUNCH_OK();
+  // No local policy (model_params['ensemble'] False, or the reference's decoder before add_local_policy: the warm-up
+  // phase of `training: joint`, CVRP/models.py:409-413): every local table is zero, so the decode kernels add exactly
+  // 0 to the global score + distance penalty whatever the local weight slots hold.
+  if (!(d->flags & ELG_FLAG_ENSEMBLE)) ELG_CUDA_OK(cudaMemsetAsync(derived + DER_LOC, 0, sizeof(float) * LOC_TOTAL, st));
   // pre-split every GEMM weight into tcgen05 operand tiles (read back by TMA in tc_gemm_kernel)
   auto split = [&](const float* w, int N, int K, long long off_floats) -> int {
     split_weights_kernel<<<148, 256, 0, st>>>(w, N, K, K, reinterpret_cast<uint8_t*>(derived + off_floats));

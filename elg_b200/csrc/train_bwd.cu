@@ -509,7 +509,7 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
     const int Rb = a.nT * M;          // rows per instance in this chunk
     ELG_TRY(launch_local(a, false, st));
     ELG_TRY(launch_global_bwd(a, st));
-    ELG_TRY(launch_local(a, true, st));
+    if (d->flags & ELG_FLAG_ENSEMBLE) ELG_TRY(launch_local(a, true, st));      // no local policy: its parameters get no gradient
     GemmP p;
     // d E'[b] += DX[b]^T O[b]
     p.A = a.dx; p.sAm = 1; p.sAk = NP; p.bA1 = (long long)Rb * NP;
@@ -518,7 +518,7 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
     p.M = N1; p.N = E; p.K = Rb; p.nb1 = B; p.nb2 = 1; p.accumulate = 1;
     ELG_TRY(launch_gemm(p, st));
   }
-  ELG_TRY(launch_local_fold_bwd(d, L, weights, derived, ws + w.lg, grads, st));
+  if (d->flags & ELG_FLAG_ENSEMBLE) ELG_TRY(launch_local_fold_bwd(d, L, weights, derived, ws + w.lg, grads, st));
 
   // ---- decoder-side tables -> encoded nodes and decoder weights
   const float* enc = t->enc;

@@ -90,9 +90,16 @@ class ModelHandle:
             raise ValueError("attention must be auto, tensor or fp32")
         self.desc.flags |= {"auto": 0, "tensor": _lib.FLAG_ATTN_TENSOR, "fp32": _lib.FLAG_ATTN_FP32}[attention]
         slots, total = weight_slots(problem, self.desc)
+        local_keys = [k for k in slots if ".local_polic" in k]
+        self.has_local = bool(self.desc.flags & _lib.FLAG_ENSEMBLE) and all(k in state_dict for k in local_keys)
+        if not self.has_local:
+            # model_params['ensemble'] False, or the reference's decoder before add_local_policy (CVRP/models.py:294-297,
+            # 409): global policy + distance penalty only; the local slots of the packed buffer stay zero
+            self.desc.flags &= ~_lib.FLAG_ENSEMBLE
+            slots = {k: o for k, o in slots.items() if k not in local_keys}
         missing = [k for k in slots if k not in state_dict]
         if missing:
-            raise KeyError("state_dict is missing %s (call decoder.add_local_policy before load_state_dict)" % missing[:3])
+            raise KeyError("state_dict is missing %s" % missing[:3])
         host = torch.zeros(total, dtype=torch.float32)
         for k, off in slots.items():
             v = state_dict[k].detach().to("cpu", torch.float32).reshape(-1)

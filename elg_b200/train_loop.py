@@ -3,9 +3,9 @@
 
 Same config.yml keys, same checkpoint dict ('step', 'model_state_dict', 'optimizer_state_dict'), same JSON log
 ('result': val_100 / val_200 / val_500 lists), same mixed-distribution sampling (softmax of the validation gaps).
-Differences, stated once: (1) the reference trains the global policy alone for the first T steps and adds the local
-policy afterwards (`training: joint`); the CUDA path implements the ensemble (joint) phase only, so steps before T are
-run jointly too and a note is printed; (2) validation files under data/ are used when present, otherwise seeded
+`training: joint` follows the reference: the global policy (+ distance penalty) trains alone until step T, then the
+local policy is added with fresh parameters and a new optimizer (CVRP/train.py:91-95); `only_global` never adds it.
+Differences, stated once: (1) `only_local` (CVRPModel_local) is not implemented; (2) validation files under data/ are used when present, otherwise seeded
 batches from the device generators stand in for them; (3) with torch.distributed initialised every rank trains on its
 own instances and the gradient is all-reduced (the reference has no multi-GPU training).
 """
@@ -86,7 +86,8 @@ def validate(problem, trainer, model_params, multiple_width, device, mixed, dist
         from .tsp import TSPEnv as Env, TSPModel as Model
         pre = 'tsp'
     model = Model(**model_params)
-    model.decoder.add_local_policy(device)
+    if trainer.has_local:
+        model.decoder.add_local_policy(device)
     model.load_state_dict(trainer.state_dict())
     model = model.to(device).requires_grad_(False)
     out = []
@@ -116,13 +117,11 @@ def train(problem, config, device, dir_path=None, log_path=None, max_steps=None,
             from .cvrp import CVRPModel as Model
         else:
             from .tsp import TSPModel as Model
-        m = Model(**model_params)
-        m.decoder.add_local_policy("cpu")
+        m = Model(**model_params)          # no local policy yet, as in the reference (CVRP/train.py:199)
         state_dict = m.state_dict()
-    if config.get('training', 'joint') != 'joint':
-        raise NotImplementedError("only `training: joint` (global + local ensemble) is implemented")
-    if verbose and p['start_steps'] < p['T']:
-        print("note: the global-only warm-up phase (steps < T) is not implemented; training jointly from step %d" % p['start_steps'])
+    training = config.get('training', 'joint')
+    if training not in ('joint', 'only_global'):
+        raise NotImplementedError("`training: %s` is not implemented (joint and only_global are)" % training)
     tr = Trainer(problem, model_params, state_dict, device, lr=p['learning_rate'], weight_decay=1e-6,
                  scale_norm=p['scale_norm'], process_group=process_group)
     rank = torch.distributed.get_rank(process_group) if tr.world > 1 else 0
@@ -134,6 +133,11 @@ def train(problem, config, device, dir_path=None, log_path=None, max_steps=None,
         n_steps = min(n_steps, max_steps)
     history = []
     for i in range(n_steps):
+        # Enable joint training (CVRP/train.py:91-95)
+        if i == p['T'] - p['start_steps'] and training == 'joint':
+            if verbose and rank == 0:
+                print("Enable joint training.")
+            tr.add_local_policy()
         if p['mixed']:
             dis = np.random.choice(['uniform', 'cluster', 'mixed'], size=1, p=softmax(gaps))
             distribution['data_type'] = dis

@@ -30,8 +30,42 @@ class Trainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self._slots, _ = engine.weight_slots(problem, self.handle.desc)
+        slots, _ = engine.weight_slots(problem, self.handle.desc)
+        self._all_slots = slots
+        self._local_keys = [k for k in slots if ".local_polic" in k]
+        self._model_params = dict(model_params)
+        # without a local policy (decoder.local False, CVRP/models.py:294-297) its keys are not part of the model
+        self._slots = slots if self.handle.has_local else {k: o for k, o in slots.items() if k not in self._local_keys}
         self._shapes = {k: tuple(v.shape) for k, v in state_dict.items() if k in self._slots}
+
+    @property
+    def has_local(self):
+        return self.handle.has_local
+
+    def add_local_policy(self, local_state_dict=None):
+        """The switch to joint training (CVRP/train.py:91-95): `model.decoder.add_local_policy(device)` with freshly
+        initialised local-policy parameters (or the given ones) and a NEW optimizer (all Adam moments and the step
+        count start again)."""
+        from . import _lib
+        from .params import LocalPolicy
+        if self.handle.has_local:
+            return
+        if local_state_dict is None:
+            lp = LocalPolicy(self.problem, dict(self._model_params, demand=self._model_params.get("demand", True)))
+            pre = "decoder.local_policies.0." if self.problem == "cvrp" else "decoder.local_policy_0."
+            local_state_dict = {pre + k: v for k, v in lp.state_dict().items()}
+        self._slots = self._all_slots
+        self._shapes.update({k: tuple(local_state_dict[k].shape) for k in self._local_keys})
+        host = self.handle.weights.detach().cpu()
+        for k in self._local_keys:
+            v = local_state_dict[k].detach().to("cpu", torch.float32).reshape(-1)
+            host[self._all_slots[k]:self._all_slots[k] + v.numel()] = v
+        self.handle.weights.copy_(host)
+        self.handle.desc.flags |= _lib.FLAG_ENSEMBLE
+        self.handle.has_local = True
+        engine.prepare_model(self.handle)
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        self.step_count = 0
 
     # ---- one forward (sample rollout) + backward; returns the pieces so tests can look at them
     def forward_backward(self, data, M, start_nodes=None, seed=0):

@@ -34,7 +34,8 @@ extern "C" {
 enum { ELG_TSP = 0, ELG_CVRP = 1 };
 enum { ELG_GREEDY = 0, ELG_SAMPLE = 1 };
 enum {
-  ELG_FLAG_ENSEMBLE = 1,          /* model_params['ensemble']          */
+  ELG_FLAG_ENSEMBLE = 1,          /* model_params['ensemble'] and the local policy is present (decoder.local); off = global
+                                     policy + distance penalty only: local tables are zeroed, local parameters get no gradient */
   ELG_FLAG_DISTANCE_PENALTY = 2,  /* model_params['distance_penalty']  */
   ELG_FLAG_POSITIONAL = 4,        /* model_params['positional']        */
   /* kernel selection for elg_rollout / elg_decode_step (diagnostics; default = automatic) */

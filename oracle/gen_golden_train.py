@@ -27,6 +27,9 @@ CASES = {
     "train_cvrp_n20": dict(problem="cvrp", n=6, N=20, M=20, seed=101, wseed=1234, gain=1.0, scale_norm=True),
     "train_cvrp_n50": dict(problem="cvrp", n=3, N=50, M=50, seed=102, wseed=7, gain=2.0, scale_norm=True),
     "train_cvrp_n100": dict(problem="cvrp", n=2, N=100, M=100, seed=103, wseed=1234, gain=1.0, scale_norm=True),
+    # decoder without add_local_policy: the warm-up phase of `training: joint` (global policy + distance penalty)
+    "train_cvrp_n20_global": dict(problem="cvrp", n=6, N=20, M=20, seed=104, wseed=1234, gain=1.0, scale_norm=True, local=False),
+    "train_tsp_n20_global": dict(problem="tsp", n=6, N=20, M=20, seed=114, wseed=1234, gain=1.0, scale_norm=True, local=False),
     "train_tsp_n20": dict(problem="tsp", n=6, N=20, M=20, seed=111, wseed=1234, gain=1.0, scale_norm=True),
     "train_tsp_n50": dict(problem="tsp", n=3, N=50, M=50, seed=112, wseed=7, gain=2.0, scale_norm=True),
 }
@@ -60,7 +63,10 @@ def worker(problem, names):
         mp = dict(DEFAULT_MODEL_PARAMS[problem])
         sd = synthetic_state_dict(problem, seed=c["wseed"], gain=c["gain"])
         model = Model(**mp)
-        model.decoder.add_local_policy("cpu")
+        if c.get("local", True):
+            model.decoder.add_local_policy("cpu")
+        else:
+            sd = {k: v for k, v in sd.items() if ".local_polic" not in k}
         model.load_state_dict(sd)
         env = Env(c["M"], "cpu")
         optimizer = Optimizer(model.parameters(), lr=1e-4, weight_decay=1e-6)

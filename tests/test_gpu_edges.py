@@ -114,3 +114,38 @@ def test_out_of_envelope_fails_loudly():
     big = torch.rand(1, 8200, 2, device=DEV)
     with pytest.raises(_lib.ElgError):                                   # beyond ELG_MAX_NODES
         engine.rollout(engine.encode(handle, big), 4, [0, 1, 2, 3])
+
+
+@pytest.mark.parametrize("kind", ["cvrp", "tsp"])
+def test_model_without_local_policy_matches_oracle(kind):
+    """The reference's decoder before add_local_policy (self.local False, CVRP/models.py:409): global policy + distance
+    penalty.  The drop-in model packs no local weights, the library zeroes the local tables."""
+    import random
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    sd = {k: v for k, v in synthetic_state_dict(kind, seed=9, gain=3.0).items() if ".local_polic" not in k}
+    if kind == "cvrp":
+        from elg_b200.cvrp import CVRPEnv as Env, CVRPModel as Model, rollout
+        data = synthetic_cvrp_batch(3, 30, seed=2)
+        prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], 8)
+    else:
+        from elg_b200.tsp import TSPEnv as Env, TSPModel as Model, rollout
+        data = synthetic_tsp_batch(3, 30, seed=2)
+        prob = O.load_tsp(data, 8)
+    model = Model(**mp)                      # no add_local_policy
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    env = Env(30, DEV)
+    env.load_random_problems(data, 8)
+    reset_state, _, _ = env.reset()
+    random.seed(3)
+    model.pre_forward(reset_state)
+    tours, _, reward = rollout(model, env, "greedy")
+    W = O.Weights(sd, kind, dict(mp, ensemble=False))
+    ref_t, _, ref_r = O.rollout(W, prob, 30, O.start_permutation(kind, 30, 30, seed=3), "greedy")
+    T = max(tours.shape[2], ref_t.shape[2])
+    a = torch.zeros(24, 30, T, dtype=torch.long); a[:, :, :tours.shape[2]] = tours.cpu()
+    b = torch.zeros(24, 30, T, dtype=torch.long); b[:, :, :ref_t.shape[2]] = ref_t
+    same = (a == b).all(dim=2)
+    assert float(same.float().mean()) >= 0.97
+    assert float(((reward.cpu() - ref_r).abs() / ref_r.abs())[same].max()) < 1e-4

@@ -39,7 +39,7 @@ def test_gradient_matches_reference_training_step(name):
     mine = tr.unpack(grads)
     ef = TH.fixture_errors(g, mine)
     assert max(ef.values()) < 2e-2, sorted(ef.items(), key=lambda kv: -kv[1])[:3]
-    _, _, ref, _ = TH.oracle_grads(g.kind, g.meta["model_params"], g.state_dict(), g.problem(), g.M, tours, g.reward(),
+    _, _, ref, _ = TH.oracle_grads(g.kind, g.model_params(), g.state_dict(), g.problem(), g.M, tours, g.reward(),
                                    g.meta["scale_norm"])
     eo = TH.grad_errors(mine, ref)
     assert max(eo.values()) < 2e-2, sorted(eo.items(), key=lambda kv: -kv[1])[:3]
@@ -214,3 +214,27 @@ def test_checkpoint_resume_reproduces_the_next_step():
     assert float((a.handle.weights - b.handle.weights).abs().max()) < 2.5e-4
     sd2 = b.state_dict()
     assert all(sd2[k].shape == sd[k].shape for k in sd2)
+
+
+def test_joint_training_switches_on_the_local_policy_at_step_T(tmp_path):
+    """CVRP/train.py:91-95: global policy + distance penalty alone until step T, then add_local_policy + new optimizer."""
+    import numpy as np
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS
+    from elg_b200.train_loop import train
+    from elg_b200.trainer import Trainer
+    torch.manual_seed(5); np.random.seed(5); random.seed(5)
+    config = {"name": "t", "training": "joint", "seed": 5,
+              "params": {"problem_size": 20, "multiple_width": 20, "scale_norm": True, "T": 3, "start_steps": 0,
+                         "train_steps": 5, "mixed": False, "train_batch_size": 8, "learning_rate": 1e-4, "log_step": 100},
+              "distribution": {"data_type": "uniform", "n_cluster": 3, "n_cluster_mix": 1, "lower": 0.2, "upper": 0.8, "std": 0.07},
+              "model_params": dict(DEFAULT_MODEL_PARAMS["cvrp"])}
+    tr, hist = train("cvrp", dict(config, params=dict(config["params"], train_steps=2)), "cuda:0", verbose=False)
+    assert not tr.has_local and tr.step_count == 3 and not any("local" in k for k in tr.state_dict())
+    lo = min(tr._all_slots[k] for k in tr._local_keys)
+    assert float(tr.handle.weights[lo:].abs().max()) == 0.0            # local slots (the tail of the buffer) untouched
+    tr, hist = train("cvrp", config, "cuda:0", verbose=False)
+    assert tr.has_local and tr.step_count == 3                           # 6 steps: 3 warm-up, optimizer restarted, 3 joint
+    sd = tr.state_dict()
+    assert any("local_policies.0.Wq.weight" in k for k in sd)
+    assert float(tr.exp_avg[lo:].abs().max()) > 0.0                      # the local policy receives gradient now
+    assert len(hist) == 6 and all(np.isfinite(h[0]) for h in hist)

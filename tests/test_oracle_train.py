@@ -9,7 +9,7 @@ from train_helpers import TRAIN_CASES, TrainGolden, sample_idx
 
 
 def oracle_grads(g, dtype=torch.float32):
-    W = O.Weights(g.state_dict(), g.kind, g.meta["model_params"], dtype).requires_grad_()
+    W = O.Weights(g.state_dict(), g.kind, g.model_params(), dtype).requires_grad_()
     J, logp = O.reinforce_loss(W, g.problem(dtype), g.M, g.tours(), g.reward().to(dtype), g.meta["scale_norm"])
     J.backward()
     return W, J.detach(), logp.detach(), {k: v.grad for k, v in W.sd.items()}

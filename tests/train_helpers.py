@@ -9,7 +9,8 @@ from elg_b200.synth import state_dict_checksum, synthetic_state_dict
 from oracle import elg_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TRAIN_CASES = ["train_cvrp_n20", "train_cvrp_n50", "train_cvrp_n100", "train_tsp_n20", "train_tsp_n50"]
+TRAIN_CASES = ["train_cvrp_n20", "train_cvrp_n50", "train_cvrp_n100", "train_tsp_n20", "train_tsp_n50",
+               "train_cvrp_n20_global", "train_tsp_n20_global"]
 SAMPLE = 512
 
 
@@ -30,8 +31,17 @@ class TrainGolden:
 
     def state_dict(self):
         sd = synthetic_state_dict(self.kind, seed=self.meta["wseed"], gain=self.meta["gain"])
+        if not self.meta.get("local", True):      # reference decoder without add_local_policy
+            sd = {k: v for k, v in sd.items() if ".local_polic" not in k}
         assert state_dict_checksum(sd) == self.meta["wsum"]
         return sd
+
+    def model_params(self):
+        """model_params as the oracle needs them: `ensemble` means "a local policy is present" there."""
+        mp = dict(self.meta["model_params"])
+        if not self.meta.get("local", True):
+            mp["ensemble"] = False
+        return mp
 
     def data(self):
         z = self.z

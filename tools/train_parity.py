@@ -19,7 +19,7 @@ import train_helpers as TH                                   # noqa: E402
 def run(name, verbose=True):
     g = TH.TrainGolden(name)
     dev = "cuda:0"
-    mp = g.meta["model_params"]
+    mp = g.model_params()
     sd = g.state_dict()
     tr = Trainer(g.kind, mp, sd, dev, scale_norm=g.meta["scale_norm"])
     data = g.data()
