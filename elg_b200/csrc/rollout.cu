@@ -890,6 +890,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_kernel(const RolloutArgs A) {
             const int sl = sel[i];
             const int prev = sCur[r];
             const bool was_fin = sFin[r] != 0;
+            __syncwarp();     // every lane has read the row state (and its mask words in B3) before lane 0 rewrites it
             bool fin = was_fin;
             float ld = 1.f;
             if (CVRP) {
