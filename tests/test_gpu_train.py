@@ -238,3 +238,29 @@ def test_joint_training_switches_on_the_local_policy_at_step_T(tmp_path):
     assert any("local_policies.0.Wq.weight" in k for k in sd)
     assert float(tr.exp_avg[lo:].abs().max()) > 0.0                      # the local policy receives gradient now
     assert len(hist) == 6 and all(np.isfinite(h[0]) for h in hist)
+
+
+def test_train_py_entry_point_reads_config_yml(tmp_path):
+    """`python -m elg_b200.cvrp.train` in a directory with the reference's config.yml layout (CVRP/config.yml)."""
+    import os
+    import subprocess
+    import sys
+    import yaml
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS
+    cfg = {"name": "ELG", "use_cuda": True, "cuda_device_num": 0, "logger": "no_logger", "load_checkpoint": None,
+           "training": "joint", "seed": 924,
+           "params": {"problem_size": 20, "multiple_width": 20, "scale_norm": True, "T": 2, "start_steps": 0, "train_steps": 3,
+                      "mixed": False, "train_batch_size": 8, "test_size": 10, "test_batch_size": 10, "learning_rate": 1e-4,
+                      "log_step": 4, "aug_factor": 8},
+           "distribution": {"data_type": "uniform", "n_cluster": 3, "n_cluster_mix": 1, "lower": 0.2, "upper": 0.8, "std": 0.07},
+           "model_params": dict(DEFAULT_MODEL_PARAMS["cvrp"])}
+    with open(tmp_path / "config.yml", "w") as f:
+        yaml.safe_dump(cfg, f)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "elg_b200.cvrp.train"], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Enable joint training." in r.stdout
+    runs = os.listdir(tmp_path / "weights")
+    assert len(runs) == 1 and os.path.exists(tmp_path / "weights" / runs[0] / "model_epoch_1.pt")
+    assert len(os.listdir(tmp_path / "log")) == 1
