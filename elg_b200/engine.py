@@ -314,6 +314,8 @@ def encode_train(handle, xy, demand=None):
 
 
 _train_ws = {}
+# when set to a list, reinforce_backward() appends (start_event, end_event, row-steps differentiated)
+train_profile_events = None
 
 
 def reinforce_backward(batch, saved, M, tours, T, reward, logp=None, scale_norm=True, chunk_steps=16, grads=None):
@@ -335,9 +337,15 @@ def reinforce_backward(batch, saved, M, tours, T, reward, logp=None, scale_norm=
         grads = torch.empty_like(h.weights)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
+        if train_profile_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(dev))
         check(lib.elg_reinforce_backward(h.desc, _ptr(h.weights), _ptr(h.derived), batch.tables, _ptr(saved), B, M, N1,
                                          _ptr(tours), t_max, int(T), _ptr(reward.contiguous()), _ptr(logp), 1 if scale_norm else 0,
                                          _ptr(grads), _ptr(loss), _ptr(ws), ws.numel(), _stream(dev)))
+        if train_profile_events is not None:
+            ev1.record(torch.cuda.current_stream(dev))
+            train_profile_events.append((ev0, ev1, B * M * max(int(T) - (2 if h.problem == "cvrp" else 1), 0)))
     return grads, loss, ws
 
 
