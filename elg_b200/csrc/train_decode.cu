@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   float* sdeb = swl + 128;              // [128]  d eb of this CTA (shared-memory atomics)
   float* pw = sdeb + 128;               // per warp: sq[128] so[128] sdo[128] sdx[128] sw[H][WS]
   __shared__ int sact[GW];
+  __shared__ uint32_t sidx_all[GW * 32];     // per warp: compact list of selectable nodes (uint8 x 128)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nTB = (A.nT + GTS - 1) / GTS;
   const int b = blockIdx.x / nTB, tb = blockIdx.x % nTB;
@@ -558,6 +559,22 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
         for (int j = lane; j < NP; j += 32) gdx[j] = 0.f;
       }
       if (act) {
+        // ---- compact list of the row's selectable nodes: every loop below runs over these only (masked nodes have
+        // weight, d logit and d score exactly 0); their count shrinks from N1 to 2 over the rollout
+        uint8_t* sidx = reinterpret_cast<uint8_t*>(sidx_all + warp * 32);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = lane + 32 * i;
+          const bool open = j < N1 && !((rc.mask[i] >> lane) & 1u);
+          const uint32_t bal = __ballot_sync(FULLM, open);
+          if (open) sidx[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)j;
+          cnt += __popc(bal);
+        }
+        // weights / d scores of masked nodes must read as zero in the accumulation phases
+        for (int i = lane; i < H * WS / 4; i += 32) reinterpret_cast<float4*>(sw)[i] = z4;
+        *reinterpret_cast<float4*>(sdx + c4) = z4;
+        if (c4 < NP) *reinterpret_cast<float4*>(gdx + c4) = z4;
         // ---- query (CVRP/models.py:336-340: Wq_last [enc[cur]; load]; TSP/models.py:258-260: q_first + Wq_last enc[cur])
         float4 q4 = *reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + c4);
         if (CVRP) {
@@ -569,6 +586,10 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
         }
         *reinterpret_cast<float4*>(sq + c4) = q4;
         __syncwarp();
+        const int nslot = (cnt + 31) >> 5;          // node slots of 32 lanes over the compact list
+        int jn[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) jn[i] = (lane + 32 * i) < cnt ? (int)sidx[lane + 32 * i] : -1;
         // ---- multi-head attention weights (log2 domain: K' carries log2(e)/sqrt(D))
 #pragma unroll 1
         for (int h = 0; h < H; ++h) {
@@ -576,9 +597,8 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
           float mx = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int j = lane + 32 * i;
             float s = -INFINITY;
-            if (j < N1 && !((rc.mask[i] >> lane) & 1u)) s = dot16(sq + h * D, sK + j * GS + h * D);
+            if (i < nslot && jn[i] >= 0) s = dot16(sq + h * D, sK + jn[i] * GS + h * D);
             sc[i] = s;
             mx = fmaxf(mx, s);
           }
@@ -589,15 +609,14 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
           sum = warp_sum(sum);
           const float inv = 1.f / sum;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = lane + 32 * i;
-            if (j < N1) sw[h * WS + j] = sc[i] * inv;
-          }
+          for (int i = 0; i < 4; ++i)
+            if (jn[i] >= 0) sw[h * WS + jn[i]] = sc[i] * inv;
         }
         __syncwarp();
         // ---- attention output o[c], lane = 4 channels of head hl
         float4 o4 = z4;
-        for (int j = 0; j < N1; ++j) {
+        for (int k = 0; k < cnt; ++k) {
+          const int j = sidx[k];
           const float wv = sw[hl * WS + j];
           const float4 v4 = *reinterpret_cast<const float4*>(sV + j * GS + c4);
           o4.x = fmaf(wv, v4.x, o4.x); o4.y = fmaf(wv, v4.y, o4.y); o4.z = fmaf(wv, v4.z, o4.z); o4.w = fmaf(wv, v4.w, o4.w);
@@ -611,9 +630,9 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
         const float* addr = A.add + row * NP;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int j = lane + 32 * i;
           lg[i] = -INFINITY; th[i] = 0.f;
-          if (j < N1 && !((rc.mask[i] >> lane) & 1u)) {
+          if (i < nslot && jn[i] >= 0) {
+            const int j = jn[i];
             float s = seb[j];
             const float* er = sE + j * GS;
 #pragma unroll 8
@@ -634,22 +653,23 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
         const float cf = A.coef[(size_t)b * M + m];
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int j = lane + 32 * i;
-          float dxv = 0.f;
-          if (lg[i] != -INFINITY) {
+          if (jn[i] >= 0) {
+            const int j = jn[i];
             const float dl = cf * ((j == rc.act ? 1.f : 0.f) - pe[i] * inv);
-            dxv = dl * A.clip * (1.f - th[i] * th[i]);
+            const float dxv = dl * A.clip * (1.f - th[i] * th[i]);
+            sdx[j] = dxv;
+            gdx[j] = dxv;
+            if (dxv != 0.f) atomicAdd(sdeb + j, dxv);
           }
-          sdx[j] = dxv;
-          if (j < NP) gdx[j] = dxv;
-          if (dxv != 0.f) atomicAdd(sdeb + j, dxv);
         }
         __syncwarp();
         // ---- d o = sum_j dx_j E'_j
         float4 d4 = z4;
-        for (int j = 0; j < N1; ++j) {
+        for (int k = 0; k < cnt; ++k) {
+          const int j = sidx[k];
           const float x = sdx[j];
           const float4 e4 = *reinterpret_cast<const float4*>(sE + j * GS + c4);
           d4.x = fmaf(x, e4.x, d4.x); d4.y = fmaf(x, e4.y, d4.y); d4.z = fmaf(x, e4.z, d4.z); d4.w = fmaf(x, e4.w, d4.w);
@@ -673,32 +693,41 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
       }
       __syncthreads();
       if (act) {
-        // ---- softmax backward per head: d s2_hj = ln2 * w_hj (d w_hj - sum_j w d w), in place over w
+        // ---- softmax backward per head: d s2_hj = ln2 * w_hj (d w_hj - sum_j w d w), in place over w (compact list)
+        const uint8_t* sidx = reinterpret_cast<const uint8_t*>(sidx_all + warp * 32);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int nb = N1 - 32 * i;
+          const uint32_t fullw = nb >= 32 ? FULLM : (nb > 0 ? ((1u << nb) - 1u) : 0u);
+          cnt += __popc(~rc.mask[i] & fullw);
+        }
+        int jn[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) jn[i] = (lane + 32 * i) < cnt ? (int)sidx[lane + 32 * i] : -1;
 #pragma unroll 1
         for (int h = 0; h < H; ++h) {
           float dw[4], wv[4];
           float part = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int j = lane + 32 * i;
             dw[i] = 0.f; wv[i] = 0.f;
-            if (j < N1) {
-              wv[i] = sw[h * WS + j];
-              dw[i] = dot16(sdo + h * D, sV + j * GS + h * D);
+            if (jn[i] >= 0) {
+              wv[i] = sw[h * WS + jn[i]];
+              dw[i] = dot16(sdo + h * D, sV + jn[i] * GS + h * D);
             }
             part = fmaf(wv[i], dw[i], part);
           }
           const float wbar = warp_sum(part);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = lane + 32 * i;
-            if (j < N1) sw[h * WS + j] = ln2 * wv[i] * (dw[i] - wbar);
-          }
+          for (int i = 0; i < 4; ++i)
+            if (jn[i] >= 0) sw[h * WS + jn[i]] = ln2 * wv[i] * (dw[i] - wbar);
         }
         __syncwarp();
         // ---- d q = sum_j d s2_hj K'_j ; scatter into the query-table gradient
         float4 g4 = z4;
-        for (int j = 0; j < N1; ++j) {
+        for (int k = 0; k < cnt; ++k) {
+          const int j = sidx[k];
           const float x = sw[hl * WS + j];
           const float4 k4 = *reinterpret_cast<const float4*>(sK + j * GS + c4);
           g4.x = fmaf(x, k4.x, g4.x); g4.y = fmaf(x, k4.y, g4.y); g4.z = fmaf(x, k4.z, g4.z); g4.w = fmaf(x, k4.w, g4.w);
