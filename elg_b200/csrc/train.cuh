@@ -58,8 +58,8 @@ struct DecodeBwdArgs {
   // materialised per row-step (row = (b * nT + (t - t0)) * M + m)
   float* add;                 // [rows][NP]      penalty + local score per node
   float* dx;                  // [rows][NP]      d loss / d pre-tanh score
-  float* o;                   // [rows][E]       attention output (d E' = DX^T O)
   // accumulators
+  float* dEp;                 // [B][N1][E]  (w.r.t. E' = enc Wo-fold / sqrt(E))
   float* dV;                  // [B][N1][E]
   float* dK;                  // [B][N1][E]  (w.r.t. K' = K log2(e)/sqrt(D))
   float* deb;                 // [B][N1]

@@ -426,7 +426,7 @@ static TrainWs train_ws(const elg_model_desc* d, int B, int M, int N1, int t_max
   w.total = o;
   return w;
 }
-static inline long long chunk_row_floats(int NP) { return (long long)E + 2LL * NP; }
+static inline long long chunk_row_floats(int NP) { return 2LL * NP; }
 
 }  // namespace elg
 
@@ -497,26 +497,17 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
   a.problem = d->problem; a.B = B; a.M = M; a.N1 = N1; a.NP = NP; a.k_local = d->local_k; a.flags = d->flags;
   a.xi = d->xi; a.clip = d->clip; a.rec = rec; a.T = T; a.coef = coef;
   a.dqtab = ws + w.dqtab; a.dqfirst = cvrp ? nullptr : ws + w.dqfirst; a.dwl = ws + w.dwl; a.lg = ws + w.lg;
-  a.dV = ws + w.dV; a.dK = ws + w.dK; a.deb = ws + w.deb;
+  a.dV = ws + w.dV; a.dK = ws + w.dK; a.deb = ws + w.deb; a.dEp = ws + w.dEp;
   const long long crow = (long long)B * nT * M;
   float* cb = ws + w.chunk;
   a.add = cb; cb += crow * NP;
-  a.dx = cb; cb += crow * NP;
-  a.o = cb;
+  a.dx = cb;
   for (int t0 = cvrp ? 2 : 1; t0 < T; t0 += nT) {
     a.t0 = t0;
     a.nT = (T - t0) < nT ? (T - t0) : nT;
-    const int Rb = a.nT * M;          // rows per instance in this chunk
     ELG_TRY(launch_local(a, false, st));
     ELG_TRY(launch_global_bwd(a, st));
     if (d->flags & ELG_FLAG_ENSEMBLE) ELG_TRY(launch_local(a, true, st));      // no local policy: its parameters get no gradient
-    GemmP p;
-    // d E'[b] += DX[b]^T O[b]
-    p.A = a.dx; p.sAm = 1; p.sAk = NP; p.bA1 = (long long)Rb * NP;
-    p.B = a.o; p.sBk = E; p.sBn = 1; p.bB1 = (long long)Rb * E;
-    p.C = ws + w.dEp; p.ldc = E; p.bC1 = (long long)N1 * E;
-    p.M = N1; p.N = E; p.K = Rb; p.nb1 = B; p.nb2 = 1; p.accumulate = 1;
-    ELG_TRY(launch_gemm(p, st));
   }
   if (d->flags & ELG_FLAG_ENSEMBLE) ELG_TRY(launch_local_fold_bwd(d, L, weights, derived, ws + w.lg, grads, st));
 

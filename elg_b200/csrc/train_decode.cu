@@ -476,6 +476,26 @@ __device__ __forceinline__ float dot16(const float* __restrict__ a, const float*
   return s;
 }
 
+// NC consecutive 32-bit tensor-memory columns of this thread's lane <-> registers
+template <int NC>
+__device__ __forceinline__ void tmem_load(uint32_t taddr, float (&v)[NC]) {
+  uint32_t r[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c += 8) umma::ld8_nw(taddr + c, r + c);
+  umma::wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) v[c] = umma::after_wait(r[c]);
+}
+template <int NC>
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const float (&v)[NC]) {
+  uint32_t r[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) r[c] = __float_as_uint(v[c]);
+#pragma unroll
+  for (int c = 0; c < NC; c += 8) umma::st8(taddr + c, r + c);
+  umma::wait_st();
+}
+
 constexpr int GTS = 4;         // rollout steps per CTA (tables staged once, accumulators flushed once)
 
 // Per 8-row batch: phase 1a (warp = row) query, attention weights, attention output, scores, softmax, d logits, d o;
@@ -523,9 +543,22 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   __syncthreads();
   const int c4 = lane * 4, hl = lane >> 2;
   float4 dwl_acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 accV[GNJ], accK[GNJ];
+  // d V, d K', d E' accumulators of this thread (GNJ nodes x 4 channels each) live in tensor memory: 2 KB per thread
+  // that nothing else uses here, read-modify-written once per 12-row batch with tcgen05.ld / tcgen05.st
+  constexpr int NC = GNJ * 4;
+  static_assert(NC % 8 == 0 && 3 * NC * ((GW + 3) / 4) <= 512, "tensor-memory budget");
+  __shared__ uint32_t s_tmem;
+  if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tacc = s_tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * (3 * NC);
+  {
+    uint32_t zr[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int i = 0; i < GNJ; ++i) accV[i] = accK[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 3 * NC; c += 8) umma::st8(tacc + c, zr);
+    umma::wait_st();
+  }
   const float ln2 = 0.6931471805599453f;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int tl_end = min(A.nT, tb * GTS + GTS);
@@ -535,11 +568,7 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
     int any = 0;
     for (int m = tid; m < M; m += GW * 32) any |= recs[m].active;
     any = __syncthreads_or(any);
-    if (!any) {      // the batched GEMM reads every row of the chunk: zero this step's rows
-      for (size_t i = tid; i < (size_t)M * E / 4; i += GW * 32) reinterpret_cast<float4*>(A.o + row0 * E)[i] = z4;
-      for (size_t i = tid; i < (size_t)M * NP / 4; i += GW * 32) reinterpret_cast<float4*>(A.dx + row0 * NP)[i] = z4;
-      continue;
-    }
+    if (!any) continue;      // local_kernel<BWD> skips inactive rows as well, so their DX rows are never read
     for (int m0 = 0; m0 < M; m0 += GW) {
       const int m = m0 + warp;
       const bool valid = m < M;
@@ -549,15 +578,10 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
       const bool act = valid && rc.active;
       if (lane == 0) sact[warp] = act ? 1 : 0;
       const size_t row = row0 + m;
-      float* go = A.o + row * E;
       float* gdx = A.dx + row * NP;
       const int cur = rc.cur;
       const float load = CVRP ? rc.load : 0.f;
       const int first = CVRP ? 0 : __float_as_int(rc.load);
-      if (valid && !act) {
-        *reinterpret_cast<float4*>(go + c4) = z4;
-        for (int j = lane; j < NP; j += 32) gdx[j] = 0.f;
-      }
       if (act) {
         // ---- compact list of the row's selectable nodes: every loop below runs over these only (masked nodes have
         // weight, d logit and d score exactly 0); their count shrinks from N1 to 2 over the rollout
@@ -622,7 +646,6 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
           o4.x = fmaf(wv, v4.x, o4.x); o4.y = fmaf(wv, v4.y, o4.y); o4.z = fmaf(wv, v4.z, o4.z); o4.w = fmaf(wv, v4.w, o4.w);
         }
         *reinterpret_cast<float4*>(so + c4) = o4;
-        *reinterpret_cast<float4*>(go + c4) = o4;
         __syncwarp();
         // ---- scores, clipping, softmax over the nodes, d logits
         float th[4], lg[4];
@@ -677,19 +700,43 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
         *reinterpret_cast<float4*>(sdo + c4) = d4;
       }
       __syncthreads();
-      // ---- phase 2a: d V[j][c] += w_r[h(c)][j] d o_r[c] over the rows of the batch (warp = nodes warp, warp+8, ...)
+      // ---- phase 2a: d V[j][c] += w_r[h(c)][j] d o_r[c] over the rows of the batch (warp = nodes warp, warp+GW, ...)
+      {
+        float acc[NC];
+        tmem_load<NC>(tacc, acc);
 #pragma unroll 1
-      for (int r = 0; r < GW; ++r) {
-        if (!sact[r]) continue;
-        const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
-        const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + 2 * 128 + c4);
+        for (int r = 0; r < GW; ++r) {
+          if (!sact[r]) continue;
+          const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
+          const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + 2 * 128 + c4);
 #pragma unroll
-        for (int i = 0; i < GNJ; ++i) {
-          const int j = warp + GW * i;
-          const float wv = j < N1 ? rw[j] : 0.f;
-          accV[i].x = fmaf(wv, g4.x, accV[i].x); accV[i].y = fmaf(wv, g4.y, accV[i].y);
-          accV[i].z = fmaf(wv, g4.z, accV[i].z); accV[i].w = fmaf(wv, g4.w, accV[i].w);
+          for (int i = 0; i < GNJ; ++i) {
+            const int j = warp + GW * i;
+            const float wv = j < N1 ? rw[j] : 0.f;
+            acc[4 * i + 0] = fmaf(wv, g4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(wv, g4.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(wv, g4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(wv, g4.w, acc[4 * i + 3]);
+          }
         }
+        tmem_store<NC>(tacc, acc);
+      }
+      // ---- phase 2c: d E'[j][c] += dx_r[j] o_r[c]
+      {
+        float acc[NC];
+        tmem_load<NC>(tacc + 2 * NC, acc);
+#pragma unroll 1
+        for (int r = 0; r < GW; ++r) {
+          if (!sact[r]) continue;
+          const float* rx = pw + r * PWF + 3 * 128;
+          const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + 128 + c4);
+#pragma unroll
+          for (int i = 0; i < GNJ; ++i) {
+            const int j = warp + GW * i;
+            const float xv = j < N1 ? rx[j] : 0.f;
+            acc[4 * i + 0] = fmaf(xv, g4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(xv, g4.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(xv, g4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(xv, g4.w, acc[4 * i + 3]);
+          }
+        }
+        tmem_store<NC>(tacc + 2 * NC, acc);
       }
       __syncthreads();
       if (act) {
@@ -744,33 +791,41 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
       }
       __syncthreads();
       // ---- phase 2b: d K'[j][c] += d s_r[h(c)][j] q_r[c]
+      {
+        float acc[NC];
+        tmem_load<NC>(tacc + NC, acc);
 #pragma unroll 1
-      for (int r = 0; r < GW; ++r) {
-        if (!sact[r]) continue;
-        const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
-        const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + c4);
+        for (int r = 0; r < GW; ++r) {
+          if (!sact[r]) continue;
+          const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
+          const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + c4);
 #pragma unroll
-        for (int i = 0; i < GNJ; ++i) {
-          const int j = warp + GW * i;
-          const float wv = j < N1 ? rw[j] : 0.f;
-          accK[i].x = fmaf(wv, g4.x, accK[i].x); accK[i].y = fmaf(wv, g4.y, accK[i].y);
-          accK[i].z = fmaf(wv, g4.z, accK[i].z); accK[i].w = fmaf(wv, g4.w, accK[i].w);
+          for (int i = 0; i < GNJ; ++i) {
+            const int j = warp + GW * i;
+            const float wv = j < N1 ? rw[j] : 0.f;
+            acc[4 * i + 0] = fmaf(wv, g4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(wv, g4.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(wv, g4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(wv, g4.w, acc[4 * i + 3]);
+          }
         }
+        tmem_store<NC>(tacc + NC, acc);
       }
       __syncthreads();
     }
   }
-  // ---- flush
-  float* gV = A.dV + (size_t)b * N1 * E;
-  float* gK = A.dK + (size_t)b * N1 * E;
+  // ---- flush: tensor memory -> global accumulators
+#pragma unroll 1
+  for (int mi = 0; mi < 3; ++mi) {
+    float acc[NC];
+    tmem_load<NC>(tacc + mi * NC, acc);
+    float* gM = (mi == 0 ? A.dV : (mi == 1 ? A.dK : A.dEp)) + (size_t)b * N1 * E;
 #pragma unroll
-  for (int i = 0; i < GNJ; ++i) {
-    const int j = warp + GW * i;
-    if (j < N1) {
-      float* pv = gV + j * E + c4;
-      float* pk = gK + j * E + c4;
-      atomicAdd(pv + 0, accV[i].x); atomicAdd(pv + 1, accV[i].y); atomicAdd(pv + 2, accV[i].z); atomicAdd(pv + 3, accV[i].w);
-      atomicAdd(pk + 0, accK[i].x); atomicAdd(pk + 1, accK[i].y); atomicAdd(pk + 2, accK[i].z); atomicAdd(pk + 3, accK[i].w);
+    for (int i = 0; i < GNJ; ++i) {
+      const int j = warp + GW * i;
+      if (j < N1) {
+        float* pm = gM + j * E + c4;
+        atomicAdd(pm + 0, acc[4 * i + 0]); atomicAdd(pm + 1, acc[4 * i + 1]);
+        atomicAdd(pm + 2, acc[4 * i + 2]); atomicAdd(pm + 3, acc[4 * i + 3]);
+      }
     }
   }
   __syncthreads();
@@ -779,6 +834,9 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
     atomicAdd(A.dwl + c4 + 0, dwl_acc.x); atomicAdd(A.dwl + c4 + 1, dwl_acc.y);
     atomicAdd(A.dwl + c4 + 2, dwl_acc.z); atomicAdd(A.dwl + c4 + 3, dwl_acc.w);
   }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(s_tmem, 512);
 }
 
 template <bool CVRP, int GW>
