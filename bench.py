@@ -462,7 +462,7 @@ def main():
     ap.add_argument("--workload", default="inference", choices=["inference", "train"],
                     help="inference = BASELINE.json configs[1] (the headline metric); train = configs[2]")
     ap.add_argument("--train-batch", type=int, default=64, help="training instances per step per GPU")
-    ap.add_argument("--chunk-steps", type=int, default=32, help="rollout steps per decode-backward launch")
+    ap.add_argument("--chunk-steps", type=int, default=128, help="rollout steps per decode-backward launch")
     ap.add_argument("--cpu-train-sample", type=int, default=2, help="instances in the CPU training-step sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("ELG_BENCH_ALLOW_SHORT"):

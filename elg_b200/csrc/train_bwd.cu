@@ -471,7 +471,7 @@ int elg_reinforce_backward(const elg_model_desc* d, const float* weights, const 
   const float* sv = reinterpret_cast<const float*>(saved);
   const long long avail = (long long)(workspace_bytes / sizeof(float)) - w.chunk - 64;
   int nT = (int)(avail / ((long long)B * M * chunk_row_floats(NP)));
-  if (nT > 64) nT = 64;
+  if (nT > 256) nT = 256;
   if (nT > T) nT = T;
   ELG_REQUIRE(nT >= 1, ELG_ENOMEM, "workspace too small for one step");
 

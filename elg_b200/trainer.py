@@ -16,7 +16,7 @@ from .dist import allreduce_mean_gradient
 
 class Trainer:
     def __init__(self, problem, model_params, state_dict, device, lr=1e-4, weight_decay=1e-6, scale_norm=True,
-                 betas=(0.9, 0.999), eps=1e-8, chunk_steps=32, process_group=None):
+                 betas=(0.9, 0.999), eps=1e-8, chunk_steps=128, process_group=None):
         self.problem = problem
         self.handle = engine.ModelHandle(problem, model_params, state_dict, device, attention="fp32")
         self.device = self.handle.device
