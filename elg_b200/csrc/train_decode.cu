@@ -496,7 +496,7 @@ __device__ __forceinline__ void tmem_store(uint32_t taddr, const float (&v)[NC])
   umma::wait_st();
 }
 
-constexpr int GTS = 4;         // rollout steps per CTA (tables staged once, accumulators flushed once)
+constexpr int GTS = 2;         // rollout steps per CTA (tables staged once, accumulators flushed once)
 
 // Per 8-row batch: phase 1a (warp = row) query, attention weights, attention output, scores, softmax, d logits, d o;
 // phase 2a (warp = node slice, lane = 4 channels) d V += w^T d o over the batch's rows; phase 1b softmax backward
