@@ -146,7 +146,7 @@ static int gemm_tn_acc(const float* A, int lda, const float* Bm, int ldb, float*
   p.A = A; p.B = Bm; p.C = C; p.M = M; p.N = N; p.K = (int)rows;
   p.sAm = 1; p.sAk = lda; p.sBk = ldb; p.sBn = 1; p.ldc = ldc; p.alpha = alpha; p.accumulate = 1;
   const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
-  int splits = (int)((rows + 255) / 256);
+  int splits = (int)((rows + 95) / 96);
   const int cap = (148 * 4 + tiles - 1) / tiles;
   if (splits > cap) splits = cap;
   if (splits < 1) splits = 1;
