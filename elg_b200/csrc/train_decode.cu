@@ -700,43 +700,48 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
         *reinterpret_cast<float4*>(sdo + c4) = d4;
       }
       __syncthreads();
-      // ---- phase 2a: d V[j][c] += w_r[h(c)][j] d o_r[c] over the rows of the batch (warp = nodes warp, warp+GW, ...)
+      // ---- phase 2a: d V[j][c] += w_r[h(c)][j] d o_r[c] and d E'[j][c] += dx_r[j] o_r[c] over the rows of the batch
+      // (warp = nodes warp, warp + GW, ...; both accumulators fetched from tensor memory with one wait)
       {
-        float acc[NC];
-        tmem_load<NC>(tacc, acc);
+        float accv[NC], acce[NC];
+        {
+          uint32_t r0[NC], r1[NC];
+#pragma unroll
+          for (int c = 0; c < NC; c += 8) umma::ld8_nw(tacc + c, r0 + c);
+#pragma unroll
+          for (int c = 0; c < NC; c += 8) umma::ld8_nw(tacc + 2 * NC + c, r1 + c);
+          umma::wait_ld();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) { accv[c] = umma::after_wait(r0[c]); acce[c] = umma::after_wait(r1[c]); }
+        }
 #pragma unroll 1
         for (int r = 0; r < GW; ++r) {
           if (!sact[r]) continue;
           const float* rw = pw + r * PWF + 4 * 128 + hl * WS;
+          const float* rx = pw + r * PWF + 3 * 128;
           const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + 2 * 128 + c4);
+          const float4 o4 = *reinterpret_cast<const float4*>(pw + r * PWF + 128 + c4);
 #pragma unroll
           for (int i = 0; i < GNJ; ++i) {
             const int j = warp + GW * i;
             const float wv = j < N1 ? rw[j] : 0.f;
-            acc[4 * i + 0] = fmaf(wv, g4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(wv, g4.y, acc[4 * i + 1]);
-            acc[4 * i + 2] = fmaf(wv, g4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(wv, g4.w, acc[4 * i + 3]);
-          }
-        }
-        tmem_store<NC>(tacc, acc);
-      }
-      // ---- phase 2c: d E'[j][c] += dx_r[j] o_r[c]
-      {
-        float acc[NC];
-        tmem_load<NC>(tacc + 2 * NC, acc);
-#pragma unroll 1
-        for (int r = 0; r < GW; ++r) {
-          if (!sact[r]) continue;
-          const float* rx = pw + r * PWF + 3 * 128;
-          const float4 g4 = *reinterpret_cast<const float4*>(pw + r * PWF + 128 + c4);
-#pragma unroll
-          for (int i = 0; i < GNJ; ++i) {
-            const int j = warp + GW * i;
             const float xv = j < N1 ? rx[j] : 0.f;
-            acc[4 * i + 0] = fmaf(xv, g4.x, acc[4 * i + 0]); acc[4 * i + 1] = fmaf(xv, g4.y, acc[4 * i + 1]);
-            acc[4 * i + 2] = fmaf(xv, g4.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(xv, g4.w, acc[4 * i + 3]);
+            accv[4 * i + 0] = fmaf(wv, g4.x, accv[4 * i + 0]); accv[4 * i + 1] = fmaf(wv, g4.y, accv[4 * i + 1]);
+            accv[4 * i + 2] = fmaf(wv, g4.z, accv[4 * i + 2]); accv[4 * i + 3] = fmaf(wv, g4.w, accv[4 * i + 3]);
+            acce[4 * i + 0] = fmaf(xv, o4.x, acce[4 * i + 0]); acce[4 * i + 1] = fmaf(xv, o4.y, acce[4 * i + 1]);
+            acce[4 * i + 2] = fmaf(xv, o4.z, acce[4 * i + 2]); acce[4 * i + 3] = fmaf(xv, o4.w, acce[4 * i + 3]);
           }
         }
-        tmem_store<NC>(tacc + 2 * NC, acc);
+        {
+          uint32_t r0[NC], r1[NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) { r0[c] = __float_as_uint(accv[c]); r1[c] = __float_as_uint(acce[c]); }
+#pragma unroll
+          for (int c = 0; c < NC; c += 8) umma::st8(tacc + c, r0 + c);
+#pragma unroll
+          for (int c = 0; c < NC; c += 8) umma::st8(tacc + 2 * NC + c, r1 + c);
+          umma::wait_st();
+        }
       }
       __syncthreads();
       if (act) {
