@@ -56,3 +56,77 @@ def generate_vrp_data(batch_size, problem_size, distribution, device="cuda:0", s
 
 def generate_tsp_data(batch_size, problem_size, distribution, device="cuda:0", seed=None):
     return _gen(ELG_TSP, batch_size, problem_size, distribution, device, seed, 1.0)[1]
+
+
+# ---------------------------------------------------------------------------------------------- datasets
+# The reference's Dataset classes (CVRP/generate_data.py:108-171, TSP/generate_data.py:74-99): same constructor,
+# same items; files are read on the host, generated data comes from the device generators above.
+import os
+import pickle
+
+from torch.utils.data import Dataset
+
+
+def check_extension(filename):
+    return filename if os.path.splitext(filename)[1] == ".pkl" else filename + ".pkl"
+
+
+def save_dataset(dataset, filename):
+    filedir = os.path.split(filename)[0]
+    if filedir and not os.path.isdir(filedir):
+        os.makedirs(filedir)
+    with open(check_extension(filename), 'wb') as f:
+        pickle.dump(dataset, f, pickle.HIGHEST_PROTOCOL)
+
+
+def make_instance(args):
+    depot, loc, demand, capacity, *args = args
+    grid_size = 1
+    if len(args) > 0:
+        depot_types, customer_types, grid_size = args
+    return {'loc': torch.tensor(loc, dtype=torch.float) / grid_size,
+            'demand': torch.tensor(demand, dtype=torch.float) / capacity,
+            'depot': torch.tensor(depot, dtype=torch.float) / grid_size}
+
+
+class VRPDataset(Dataset):
+    def __init__(self, filename=None, size=100, num_samples=10000, offset=0, distribution=None, device="cuda:0", seed=None):
+        super(VRPDataset, self).__init__()
+        if filename is not None:
+            assert os.path.splitext(filename)[1] == '.pkl'
+            with open(filename, 'rb') as f:
+                data = pickle.load(f)
+            self.data = [make_instance(args) for args in data[offset:offset + num_samples]]
+        else:
+            dist = distribution if distribution is not None else {"data_type": "uniform"}
+            data = generate_vrp_data(num_samples, size, dist, device, seed)
+            self.data = [make_instance([data['depot'][i, 0].cpu().numpy(), data['loc'][i].cpu().numpy(),
+                                        data['demand'][i].cpu().numpy(), 1.0]) for i in range(num_samples)]
+        self.size = len(self.data)
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+
+class TSPDataset(Dataset):
+    def __init__(self, filename=None, size=100, num_samples=10000, offset=0, distribution=None, device="cuda:0", seed=None):
+        super(TSPDataset, self).__init__()
+        if filename is not None:
+            assert os.path.splitext(filename)[1] == '.pkl'
+            with open(filename, 'rb') as f:
+                data = pickle.load(f)
+            self.data = [torch.FloatTensor(row) for row in data[offset:offset + num_samples]]
+        else:
+            dist = distribution if distribution is not None else {"data_type": "uniform"}
+            data = generate_tsp_data(num_samples, size, dist, device, seed).cpu()
+            self.data = [data[i] for i in range(num_samples)]
+        self.size = len(self.data)
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, idx):
+        return self.data[idx]

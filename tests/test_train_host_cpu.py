@@ -55,3 +55,22 @@ def test_training_modes_other_than_joint_are_rejected():
            "distribution": {"data_type": "uniform"}, "model_params": dict(DEFAULT_MODEL_PARAMS["cvrp"])}
     with pytest.raises(NotImplementedError):
         train("cvrp", cfg, "cuda:0", verbose=False)
+
+
+def test_dataset_classes_read_reference_pickles(tmp_path):
+    """VRPDataset / TSPDataset (CVRP/generate_data.py:108-171, TSP/generate_data.py:74-99) on files in the reference's
+    pickle layout: [(depot, loc, demand, capacity), ...] and [[[x, y], ...], ...]; DataLoader collation as in test.py."""
+    from torch.utils.data import DataLoader
+    from elg_b200.generate_data import TSPDataset, VRPDataset, save_dataset
+    rng = np.random.RandomState(0)
+    vrp = [(rng.rand(2).tolist(), rng.rand(10, 2).tolist(), rng.randint(1, 10, 10).tolist(), 20.0) for _ in range(5)]
+    save_dataset(vrp, str(tmp_path / "d" / "vrp10"))
+    ds = VRPDataset(str(tmp_path / "d" / "vrp10.pkl"), num_samples=4, offset=1)
+    assert len(ds) == 4 and ds[0]['loc'].shape == (10, 2) and ds[0]['depot'].shape == (2,)
+    assert torch.allclose(ds[0]['demand'], torch.tensor(vrp[1][2], dtype=torch.float) / 20.0)
+    batch = next(iter(DataLoader(ds, batch_size=4)))
+    assert batch['loc'].shape == (4, 10, 2) and batch['demand'].shape == (4, 10) and batch['depot'].shape == (4, 2)
+    tsp = rng.rand(6, 12, 2).tolist()
+    save_dataset(tsp, str(tmp_path / "d" / "tsp12.pkl"))
+    dt = TSPDataset(str(tmp_path / "d" / "tsp12.pkl"), num_samples=6)
+    assert len(dt) == 6 and next(iter(DataLoader(dt, batch_size=3))).shape == (3, 12, 2)
