@@ -59,16 +59,20 @@ __device__ __forceinline__ void warp_allreduce(float (&v)[N]) {
 }
 
 // ---- replay: the environment (CVRPEnv.step CVRP/CVRPEnv.py:190-249, TSPEnv.step TSP/TSPEnv.py:108-133) driven by the
-// recorded actions; one thread per POMO row.  Same fp32 load recurrence and masks as phase C of the rollout kernels.
-__global__ void replay_kernel(int problem, const float* __restrict__ demand, const int16_t* __restrict__ tours,
-                              int t_max, int B, int M, int N1, int T, StepRec* __restrict__ rec) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// recorded actions; one warp per POMO row.  Same fp32 load recurrence and masks as phase C of the rollout kernels.
+__global__ void __launch_bounds__(128) replay_kernel(int problem, const float* __restrict__ demand, const int16_t* __restrict__ tours,
+                                                     int t_max, int B, int M, int N1, int T, StepRec* __restrict__ rec) {
+  // one warp per POMO row; lane i owns node 32 w + i of every mask word (the too-large test is a ballot)
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= B * M) return;
   const int b = g / M, m = g % M;
   const bool cvrp = problem == ELG_CVRP;
   const float* dem = cvrp ? demand + (size_t)b * N1 : nullptr;
   const int16_t* tour = tours + (size_t)g * t_max;
   const int W = (N1 + 31) / 32;
+  float dj[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) dj[w] = (cvrp && w * 32 + lane < N1) ? dem[w * 32 + lane] : -1.f;      // -1: never too large
   uint32_t vis[4] = {0, 0, 0, 0}, msk[4] = {0, 0, 0, 0};
   float load = 1.f;
   bool fin = false;
@@ -76,37 +80,39 @@ __global__ void replay_kernel(int problem, const float* __restrict__ demand, con
   const int tpol = cvrp ? 2 : 1;
   for (int t = 0; t < T; ++t) {
     const int act = t < t_max ? (int)tour[t] : 0;
-    StepRec r;
-    r.cur = cur;
-    r.act = act;
-    r.load = cvrp ? load : __int_as_float(first);
-    int open = 0;
-    for (int w = 0; w < W; ++w) {
-      const int nb = N1 - w * 32;
-      const uint32_t fullw = nb >= 32 ? FULLM : ((1u << nb) - 1u);
-      open += __popc(~msk[w] & fullw);
-    }
-    r.active = (t >= tpol && !fin && open >= 2) ? 1 : 0;
+    if (lane == 0) {
+      StepRec r;
+      r.cur = cur;
+      r.act = act;
+      r.load = cvrp ? load : __int_as_float(first);
+      int open = 0;
+      for (int w = 0; w < W; ++w) {
+        const int nb = N1 - w * 32;
+        const uint32_t fullw = nb >= 32 ? FULLM : ((1u << nb) - 1u);
+        open += __popc(~msk[w] & fullw);
+      }
+      r.active = (t >= tpol && !fin && open >= 2) ? 1 : 0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) r.mask[w] = msk[w];
-    rec[((size_t)b * T + t) * M + m] = r;
-    // environment step
+      for (int w = 0; w < 4; ++w) r.mask[w] = msk[w];
+      rec[((size_t)b * T + t) * M + m] = r;
+    }
+    // environment step (every lane keeps the same scalar state)
     if (cvrp) {
       const bool at_depot = act == 0;
       load = at_depot ? 1.f : load - dem[act];
       vis[act >> 5] |= 1u << (act & 31);
       vis[0] = at_depot ? (vis[0] | 1u) : (vis[0] & ~1u);
       bool allv = true;
-      for (int w = 0; w < W; ++w) {
-        uint32_t big = 0;
-        for (int i = 0; i < 32; ++i) {
-          const int j = w * 32 + i;
-          if (j < N1 && __fadd_rn(load, 1e-6f) < dem[j]) big |= 1u << i;
+      const float lde = __fadd_rn(load, 1e-6f);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        if (w < W) {
+          const uint32_t big = __ballot_sync(FULLM, lde < dj[w]);
+          const int nb = N1 - w * 32;
+          const uint32_t fullw = nb >= 32 ? FULLM : ((1u << nb) - 1u);
+          allv = allv && ((vis[w] & fullw) == fullw);
+          msk[w] = vis[w] | big;
         }
-        const int nb = N1 - w * 32;
-        const uint32_t fullw = nb >= 32 ? FULLM : ((1u << nb) - 1u);
-        allv = allv && ((vis[w] & fullw) == fullw);
-        msk[w] = vis[w] | big;
       }
       fin = fin || allv;
       if (fin) msk[0] &= ~1u;
@@ -121,7 +127,7 @@ __global__ void replay_kernel(int problem, const float* __restrict__ demand, con
 
 int launch_replay(int problem, const float* demand, const int16_t* tours, int t_max, int B, int M, int N1, int T,
                   StepRec* rec, cudaStream_t st) {
-  replay_kernel<<<(B * M + 127) / 128, 128, 0, st>>>(problem, demand, tours, t_max, B, M, N1, T, rec);
+  replay_kernel<<<(B * M + 3) / 4, 128, 0, st>>>(problem, demand, tours, t_max, B, M, N1, T, rec);
   ELG_LAUNCH_OK();
   return ELG_OK;
 }
