@@ -852,7 +852,10 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
 
 template <bool CVRP, int GW>
 static int launch_global_bwd_t(const DecodeBwdArgs& a, cudaStream_t st) {
-  const size_t smem = ((size_t)3 * a.N1 * GS + 384 + (size_t)GW * (4 * 128 + H * WS)) * sizeof(float);
+  size_t smem = ((size_t)3 * a.N1 * GS + 384 + (size_t)GW * (4 * 128 + H * WS)) * sizeof(float);
+  // every CTA allocates all 512 tensor-memory columns: keep it to one CTA per SM (a second one would sit in
+  // tcgen05.alloc until the first is done), also for small instances whose tables would leave room for two
+  if (smem < 116 * 1024) smem = 116 * 1024;
   ELG_REQUIRE(smem <= 226 * 1024, ELG_EUNSUPPORTED, "training supports up to %d nodes (needs %zu bytes of shared memory)", TRAIN_MAX_NODES, smem);
   ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<CVRP, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(a.B * ((a.nT + GTS - 1) / GTS));
