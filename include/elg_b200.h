@@ -225,7 +225,7 @@ int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M
  *   reward     [B][M];  logp [B][M] (only used for the reported loss, may be NULL);  loss: one float (may be NULL)
  *   scale_norm config params.scale_norm (tsp: applied only if every instance has a non-zero maximum advantage)
  *   workspace  256-byte aligned, at least elg_train_workspace_bytes(..., chunk_steps = 1); a larger chunk_steps (up
- *              to 256; 416 bytes per row-step) lets the decode backward process that many rollout steps per launch.  Its head holds the
+ *              to 256; 832 bytes per row-step at 101 nodes) lets the decode backward process that many rollout steps per launch.  Its head holds the
  *              gradients of the decoder tables (float offsets from elg_train_workspace_layout: d E', d K', d V,
  *              d qtab, d qfirst, d eb, d w_load, local-policy accumulators), left in place for inspection.
  * Resident instances only (elg_rollout_resident() == 1: up to 112 nodes, 108 for cvrp with local_size 40). */
