@@ -264,3 +264,34 @@ def test_train_py_entry_point_reads_config_yml(tmp_path):
     runs = os.listdir(tmp_path / "weights")
     assert len(runs) == 1 and os.path.exists(tmp_path / "weights" / runs[0] / "model_epoch_1.pt")
     assert len(os.listdir(tmp_path / "log")) == 1
+
+
+def test_full_size_gradient_is_the_mean_of_shard_gradients():
+    """Size-independent property at BASELINE's full training size (64 instances x 100 rollouts, CVRP100): J is a mean
+    over instances of independent per-instance terms, so the gradient of the full batch equals the mean of the gradients
+    of its two halves replayed on the same tours (this is also what data-parallel training relies on)."""
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict
+    from elg_b200.trainer import Trainer
+    tr = Trainer("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]), synthetic_state_dict("cvrp", seed=1234, gain=1.0), "cuda:0")
+    data = synthetic_cvrp_batch(64, 100, seed=77)
+    random.seed(1)
+    out = tr.forward_backward(data, 100, seed=9)
+    full = out["grads"].clone()
+    T, tours, reward, logp = out["T"], out["tours"], out["reward"], out["logp"]
+    assert 110 <= T <= 204 and float(full.abs().max()) > 0
+    xy, dem = out["batch"].xy, out["batch"].demand
+    parts = []
+    for s in (slice(0, 32), slice(32, 64)):
+        batch, saved = engine.encode_train(tr.handle, xy[s].contiguous(), dem[s].contiguous())
+        g, loss, _ = engine.reinforce_backward(batch, saved, 100, tours[s].contiguous(), T, reward[s].contiguous(),
+                                               logp[s].contiguous(), True, 128)
+        parts.append(g.clone())
+    torch.cuda.synchronize()
+    mean = 0.5 * (parts[0] + parts[1])
+    err = float((mean - full).abs().max()) / float(full.abs().max())
+    assert err < 2e-4, err
+    # and the loss reported for the full batch is the mean of the per-row terms: J = sum coef * logp
+    adv = reward - reward.mean(dim=1, keepdim=True)
+    J = float((-(adv / adv.max(dim=1, keepdim=True)[0]) * logp).mean())
+    assert abs(float(out["loss"]) - J) < 1e-4 * max(1.0, abs(J))
