@@ -295,3 +295,27 @@ def test_full_size_gradient_is_the_mean_of_shard_gradients():
     adv = reward - reward.mean(dim=1, keepdim=True)
     J = float((-(adv / adv.max(dim=1, keepdim=True)[0]) * logp).mean())
     assert abs(float(out["loss"]) - J) < 1e-4 * max(1.0, abs(J))
+
+
+@pytest.mark.parametrize("kind", ["cvrp", "tsp"])
+def test_encode_train_equals_encode_bit_for_bit(kind):
+    """elg_encode_train runs the inference encoder's kernels with per-layer buffers: every decoder table is identical."""
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    h = engine.ModelHandle(kind, dict(DEFAULT_MODEL_PARAMS[kind]), synthetic_state_dict(kind, seed=2, gain=2.0), "cuda:0", attention="fp32")
+    if kind == "cvrp":
+        d = synthetic_cvrp_batch(5, 100, seed=3)
+        xy, dem = engine.load_problems("cvrp", d["loc"].cuda(), d["depot"].cuda(), d["demand"].cuda(), 1)
+    else:
+        xy, dem = engine.load_problems("tsp", synthetic_tsp_batch(5, 100, seed=3).cuda(), None, None, 1)
+    a = engine.encode(h, xy, dem)
+    b, saved = engine.encode_train(h, xy, dem)
+    torch.cuda.synchronize()
+    for name in ("enc", "k", "v", "qtab", "eb", "e", "nbr"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    rows = xy.shape[0] * xy.shape[1]
+    sv = saved.view(torch.float32)
+    last_t2_off = (5 * (8 * 128 + 512) + 7 * 128 + 512) * rows          # layer 5, pre-norm sum of the second sub-layer
+    t2 = sv[last_t2_off:last_t2_off + rows * 128].reshape(xy.shape[0], xy.shape[1], 128)
+    # the encoded nodes are the instance norm of that sum: zero mean / unit variance per channel before the affine map
+    assert torch.isfinite(t2).all() and float(t2.abs().max()) > 0
