@@ -568,16 +568,25 @@ __global__ void __launch_bounds__(GW * 32) global_bwd_kernel(DecodeBwdArgs A) {
   const float ln2 = 0.6931471805599453f;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int tl_end = min(A.nT, tb * GTS + GTS);
-  for (int tl = tb * GTS; tl < tl_end; ++tl) {
-    const StepRec* recs = A.rec + ((size_t)b * A.T + A.t0 + tl) * M;
-    const size_t row0 = ((size_t)b * A.nT + tl) * M;
-    int any = 0;
-    for (int m = tid; m < M; m += GW * 32) any |= recs[m].active;
-    any = __syncthreads_or(any);
-    if (!any) continue;      // local_kernel<BWD> skips inactive rows as well, so their DX rows are never read
-    for (int m0 = 0; m0 < M; m0 += GW) {
-      const int m = m0 + warp;
-      const bool valid = m < M;
+  // ---- the active rows of this CTA's steps, packed: batches of GW rows are taken from this list, so neither the tail
+  // of a step (100 rows = 8 x 12 + 4) nor the sparse late steps leave warps idle at the batch barriers
+  __shared__ uint16_t slist[GTS * 128];
+  __shared__ int s_nact;
+  if (tid == 0) s_nact = 0;
+  __syncthreads();
+  for (int e = tid; e < (tl_end - tb * GTS) * M; e += GW * 32) {
+    const int tl = tb * GTS + e / M, m = e % M;
+    if (A.rec[((size_t)b * A.T + A.t0 + tl) * M + m].active) slist[atomicAdd(&s_nact, 1)] = (uint16_t)(((tl - tb * GTS) << 8) | m);
+  }
+  __syncthreads();
+  const int nact = s_nact;
+  {
+    for (int m0 = 0; m0 < nact; m0 += GW) {
+      const bool valid = m0 + warp < nact;
+      const int item = valid ? (int)slist[m0 + warp] : 0;
+      const int tl = tb * GTS + (item >> 8), m = item & 255;
+      const StepRec* recs = A.rec + ((size_t)b * A.T + A.t0 + tl) * M;
+      const size_t row0 = ((size_t)b * A.nT + tl) * M;
       StepRec rc;
       rc.active = 0;
       if (valid) rc = recs[m];
@@ -856,6 +865,7 @@ static int launch_global_bwd_t(const DecodeBwdArgs& a, cudaStream_t st) {
   // every CTA allocates all 512 tensor-memory columns: keep it to one CTA per SM (a second one would sit in
   // tcgen05.alloc until the first is done), also for small instances whose tables would leave room for two
   if (smem < 116 * 1024) smem = 116 * 1024;
+  ELG_REQUIRE(a.M <= 128, ELG_EUNSUPPORTED, "training supports a POMO width of up to 128 rows (got %d)", a.M);
   ELG_REQUIRE(smem <= 226 * 1024, ELG_EUNSUPPORTED, "training supports up to %d nodes (needs %zu bytes of shared memory)", TRAIN_MAX_NODES, smem);
   ELG_CUDA_OK(cudaFuncSetAttribute(global_bwd_kernel<CVRP, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(a.B * ((a.nT + GTS - 1) / GTS));
