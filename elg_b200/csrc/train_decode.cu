@@ -324,20 +324,20 @@ __global__ void __launch_bounds__(LW * 32) local_kernel(DecodeBwdArgs A) {
     for (int c = 0; c < LE; ++c) mh = fmaf(S.Wo[lane][c], S.vo[warp][c], mh);
     S.vmh[warp][lane] = mh;
     __syncwarp();
-    float zc[4] = {mh * S.We[lane][0], mh * S.We[lane][1], mh * S.We[lane][2], mh * S.be[lane]};
-    warp_allreduce<4, false>(zc);
-    const float z0 = zc[0], z1 = zc[1], z2 = zc[2], c0 = zc[3];
-    float locv[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int p = min(lane + 32 * s, KT_MAX - 1);
-      float pm = 0.f;
-#pragma unroll
-      for (int c = 0; c < LE; ++c) pm = fmaf(S.vmh[warp][c], S.PE[p][c], pm);
-      locv[s] = (fmaf(z2, f2[s], fmaf(z1, f1[s], z0 * f0[s])) + c0 + pm) * isl;
-    }
     const size_t row = ((size_t)b * A.nT + tl) * M + m;
-    if (!BWD) {
+    if (!BWD) {      // the local scores themselves are only needed by the forward pass
+      float zc[4] = {mh * S.We[lane][0], mh * S.We[lane][1], mh * S.We[lane][2], mh * S.be[lane]};
+      warp_allreduce<4, false>(zc);
+      const float z0 = zc[0], z1 = zc[1], z2 = zc[2], c0 = zc[3];
+      float locv[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int p = min(lane + 32 * s, KT_MAX - 1);
+        float pm = 0.f;
+#pragma unroll
+        for (int c = 0; c < LE; ++c) pm = fmaf(S.vmh[warp][c], S.PE[p][c], pm);
+        locv[s] = (fmaf(z2, f2[s], fmaf(z1, f1[s], z0 * f0[s])) + c0 + pm) * isl;
+      }
       float* add = A.add + row * NP;
       for (int j = lane; j < NP; j += 32) add[j] = (DEP && j == 0) ? 0.f : A.xi;
       __syncwarp();
