@@ -15,7 +15,7 @@ FLAG_ENSEMBLE, FLAG_DISTANCE_PENALTY, FLAG_POSITIONAL = 1, 2, 4
 FLAG_ATTN_FP32, FLAG_ATTN_TENSOR = 8, 16
 MAX_LAYERS = 16
 NBR_STRIDE = 128
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ModelDesc(C.Structure):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ELG_ABI_VERSION 1
+#define ELG_ABI_VERSION 2   /* 2: training path, data generators */
 
 enum { ELG_TSP = 0, ELG_CVRP = 1 };
 enum { ELG_GREEDY = 0, ELG_SAMPLE = 1 };
