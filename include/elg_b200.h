@@ -228,7 +228,7 @@ int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M
  *              to 256; 832 bytes per row-step at 101 nodes) lets the decode backward process that many rollout steps per launch.  Its head holds the
  *              gradients of the decoder tables (float offsets from elg_train_workspace_layout: d E', d K', d V,
  *              d qtab, d qfirst, d eb, d w_load, local-policy accumulators), left in place for inspection.
- * Resident instances only (elg_rollout_resident() == 1: up to 112 nodes, 108 for cvrp with local_size 40). */
+ * Resident instances only (elg_rollout_resident() == 1: up to 112 nodes, 108 for cvrp with local_size 40), M <= 128. */
 size_t elg_train_saved_bytes(const elg_model_desc* desc, int B, int N1);
 int elg_encode_train(const elg_model_desc* desc, const float* weights, const float* derived, const elg_tables* t,
                      int B, int N1, void* saved, size_t saved_bytes, void* stream);
