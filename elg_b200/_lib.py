@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libelg_b200.so")
+# ELG_B200_LIB: a diagnostic build of the same sources (tools/phase_timing.py: `python -m elg_b200.build --variant timing`)
+LIB_PATH = os.environ.get("ELG_B200_LIB") or os.path.join(_HERE, "csrc", "libelg_b200.so")
 
 ELG_TSP, ELG_CVRP = 0, 1
 ELG_GREEDY, ELG_SAMPLE = 0, 1

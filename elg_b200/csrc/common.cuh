@@ -41,7 +41,13 @@ constexpr int LOC_PW = LOC_BE + LE;           // [KT_MAX][LE] sum_c' PE(p)[c'] W
 constexpr int LOC_PB = LOC_PW + KT_MAX * LE;  // [KT_MAX]     PE(p) . bo_l / sqrt(LE)
 constexpr int LOC_ZW = LOC_PB + KT_MAX;       // [LE][4]      f < 3: sum_c' We[c'][f] Wo_l[c'][c];  f = 3: sum_c' be[c'] Wo_l[c'][c]   (/ sqrt(LE))
 constexpr int LOC_ZB = LOC_ZW + LE * 4;       // [4]          We^T bo_l, be . bo_l                                                    (/ sqrt(LE))
-constexpr int LOC_TOTAL = LOC_ZB + 4;
+// the two local-policy contractions of rollout_tc.cu as tcgen05 B operands (fp16 hi | lo, K-major core matrices, one
+// 32-bit word per float slot):
+//   OP1 per local head h: rows n < 8: (Wv PE(p))[h*8 + n] over k = p < KT_MAX (rows 8..15 zero); 16 x KT_MAX, LBO 256 B
+//   OP2: rows n < K1: PW[n][k]; rows K1..K1+3: ZW[k][n - K1]; zero up to N2 = ceil16(K1 + 4); N2 x 32, LBO N2 * 16 B
+constexpr int LOC_OP1 = LOC_ZB + 4;           // [LH][hi 16*KT_MAX halves | lo]
+constexpr int LOC_OP2 = LOC_OP1 + LH * KT_MAX * 16;   // [hi N2*32 halves | lo], at most N2 = 80
+constexpr int LOC_TOTAL = LOC_OP2 + 80 * LE;
 constexpr int DER_FOLD_TOTAL = DER_LOC + LOC_TOTAL;
 // After the folds: every GEMM weight matrix pre-split into fp16 hi/lo tcgen05 B-operand tiles (one float's worth
 // of bytes per weight element).  Matrix W[N][K] -> tiles (n/128, k/64), each [hi 16 KB | lo 16 KB] in the K-major

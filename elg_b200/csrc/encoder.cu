@@ -21,7 +21,7 @@
 namespace elg {
 
 bool rollout_is_resident(const elg_model_desc* d, int N1);
-int launch_neighbours(const elg_model_desc* d, const float* xy, int B, int N1, void* nbr, cudaStream_t stream);
+int launch_neighbours(const elg_model_desc* d, const float* xy, const float* demand, int B, int N1, void* nbr, cudaStream_t stream);
 
 // ---- embedding --------------------------------------------------------------------------------
 __global__ void embed_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand,
@@ -701,7 +701,7 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
     ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 3LL * E * E, t->qfirst, nullptr, nullptr, rows, E, E, E, st));
   row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
   ELG_LAUNCH_OK();
-  if (t->nbr) ELG_TRY(launch_neighbours(d, t->xy, B, N1, t->nbr, st));
+  if (t->nbr) ELG_TRY(launch_neighbours(d, t->xy, t->demand, B, N1, t->nbr, st));
   if (saved)   // plain fp32 E' = enc (Wo/sqrt(E)) for the backward's forward recompute
     ELG_TRY(gemm<EPI_NONE>(enc, derived + DER_WET, saved + train_saved_eplain(d->layers, rows, d->ff), nullptr, nullptr, rows, E, E, E, N1, st));
   return ELG_OK;

@@ -149,6 +149,31 @@ __global__ void prepare_kernel(elg_model_desc d, elg_weight_layout_t L, const fl
     for (int k = 0; k < LE; ++k) a += (f < 3 ? (double)we[k][f] : (double)w[L.loc_be + k]) * (double)w[L.loc_bo + k];
     loc[LOC_ZB + f] = (float)(a * isl);
   }
+  // tcgen05 B operands of the two local-policy contractions (rollout_tc.cu), from the fp32 tables above
+  __syncthreads();
+  uint8_t* op1 = reinterpret_cast<uint8_t*>(loc + LOC_OP1);
+  for (int i = tid; i < LH * 16 * KT_MAX; i += nt) {
+    const int h = i / (16 * KT_MAX), n = (i / KT_MAX) % 16, p = i % KT_MAX;
+    __half hi, lo;
+    umma::split_f16(n < LD ? loc[LOC_VPE + p * LE + h * LD + n] : 0.f, hi, lo);
+    const uint32_t off = umma::elem_off(n, p, 256);
+    *reinterpret_cast<__half*>(op1 + h * (KT_MAX * 64) + off) = hi;
+    *reinterpret_cast<__half*>(op1 + h * (KT_MAX * 64) + KT_MAX * 32 + off) = lo;
+  }
+  const int K1 = d.local_k + (cvrp ? 1 : 0);
+  const int N2 = (K1 + 4 + 15) & ~15;
+  uint8_t* op2 = reinterpret_cast<uint8_t*>(loc + LOC_OP2);
+  for (int i = tid; i < N2 * LE; i += nt) {
+    const int n = i / LE, k = i % LE;
+    float v = 0.f;
+    if (n < K1) v = loc[LOC_PW + n * LE + k];
+    else if (n < K1 + 4) v = loc[LOC_ZW + k * 4 + (n - K1)];
+    __half hi, lo;
+    umma::split_f16(v, hi, lo);
+    const uint32_t off = umma::elem_off(n, k, (uint32_t)N2 * 16u);
+    *reinterpret_cast<__half*>(op2 + off) = hi;
+    *reinterpret_cast<__half*>(op2 + N2 * 64 + off) = lo;
+  }
 }
 
 // W[N][K] (fp32, leading dimension ld) -> fp16 hi/lo B-operand tiles for tc_gemm_kernel

@@ -62,7 +62,8 @@ __global__ void pairwise_dist_kernel(const float* __restrict__ xy, int B, int N1
 // for tsp) ordered by (distance from i, index).  The decode step takes the first k *valid* entries,
 // which is what torch.topk(k, largest=False) over the masked distance row yields in the reference
 // (CVRP/models.py:74,375; TSP/models.py:62,286) -- computed once instead of twice per step.
-__global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int N1, uint8_t* __restrict__ nbr) {
+__global__ void neighbour_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand, int N1,
+                                 uint8_t* __restrict__ nbr) {
   __shared__ float sd[128];
   const int i = blockIdx.x % N1, b = blockIdx.x / N1;
   const float* p = xy + (size_t)b * N1 * 2;
@@ -74,6 +75,9 @@ __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int 
   // pair features of get_cur_feature (CVRP/CVRPEnv.py:291-318, TSP/TSPEnv.py:135-156) for cur = i: distance and
   // polar angle to every node, so the decode step gathers them instead of recomputing sqrt / atan2 per neighbour
   float2* feat = reinterpret_cast<float2*>(row + ELG_NBR_STRIDE);
+  // the same values once more in list (rank) order, with the node's demand and id: one 16-byte record per list entry
+  // (rollout_tc.cu reads the records of the chosen ranks instead of chasing list byte -> pair table -> demand)
+  float4* rec = reinterpret_cast<float4*>(row + ELG_NBR_STRIDE + ELG_NBR_PAIR_BYTES(N1));
   for (int j = threadIdx.x; j < N1; j += blockDim.x) feat[j] = make_float2(sd[j], atan2f(p[2 * j + 1] - yi, p[2 * j] - xi));
   __syncthreads();
   for (int j = j0 + threadIdx.x; j < N1; j += blockDim.x) {
@@ -84,7 +88,9 @@ __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, int 
       rank += (dk < dj) || (dk == dj && k < j);
     }
     row[nbr_pos(rank)] = (uint8_t)j;
+    rec[rank] = make_float4(dj, atan2f(p[2 * j + 1] - yi, p[2 * j] - xi), demand ? demand[(size_t)b * N1 + j] : 0.f, __int_as_float(j));
   }
+  for (int e = N1 - j0 + threadIdx.x; e < N1; e += blockDim.x) rec[e] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- neighbour lists for the streaming variant (N1 > 112): uint16 ids, linear order ------------------
@@ -317,10 +323,10 @@ int elg_tour_length(const float* xy, int Bxy, const int64_t* tours, int B, int M
 // resident variant (N1 <= 112): uint8 ids, 8-way interleaved, ELG_NBR_STRIDE bytes per node;
 // streaming variant: uint16 ids in rank order, ELG_NBR16_STRIDE(NL) entries per node.
 namespace elg {
-int launch_neighbours(const elg_model_desc* d, const float* xy, int B, int N1, void* nbr, cudaStream_t stream) {
+int launch_neighbours(const elg_model_desc* d, const float* xy, const float* demand, int B, int N1, void* nbr, cudaStream_t stream) {
   const int problem = d->problem;
   if (rollout_is_resident(d, N1)) {
-    neighbour_kernel<<<(unsigned)B * N1, 128, 0, stream>>>(problem, xy, N1, reinterpret_cast<uint8_t*>(nbr));
+    neighbour_kernel<<<(unsigned)B * N1, 128, 0, stream>>>(problem, xy, problem == ELG_CVRP ? demand : nullptr, N1, reinterpret_cast<uint8_t*>(nbr));
     ELG_LAUNCH_OK();
     return ELG_OK;
   }

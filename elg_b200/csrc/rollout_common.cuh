@@ -94,7 +94,7 @@ __device__ __forceinline__ float octet_sum(float v) {
 
 // Optional per-phase cycle accounting (tools/phase_timing.py builds with -DELG_PHASE_TIMING; never in the shipped library)
 #ifdef ELG_PHASE_TIMING
-static __device__ unsigned long long g_phase_clk[8];   // one copy per translation unit
+static __device__ unsigned long long g_phase_clk[16];   // one copy per translation unit
 #define PHASE_T0() long long pt_ = clock64()
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); pclk[i] += (unsigned long long)(n_ - pt_); pt_ = n_; } } while (0)
 #else

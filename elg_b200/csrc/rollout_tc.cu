@@ -1,29 +1,38 @@
 // Tensor-core rollout kernel (resident instances, greedy decoding): the same per-step path as rollout.cu
-// (reference file:line list there), but the three dense contractions of the global POMO decoder
-// (CVRP/models.py:330-352, TSP/models.py:252-272) all run on tcgen05 with every operand that changes per
-// step living in TENSOR MEMORY:
+// (reference file:line list there), with every dense contraction of the step on tcgen05 and every operand that
+// changes per step living in TENSOR MEMORY (lane = POMO row):
 //
+//   global policy (CVRP/models.py:330-352, TSP/models.py:252-272)
 //   S_h = Q_h K_h'^T        A = Q   (TMEM, written by tcgen05.st)      B = K' fp16 hi/lo (smem, resident)
 //   O_h = P_h V_h           A = P_h (TMEM, written in place of S_h)    B = V^T fp16 hi/lo (smem, resident)
 //   score = O E'^T          A = O   (TMEM)                             B = E' fp16 hi/lo (smem, resident)
+//   local policy (CVRP/models.py:51-175, TSP/models.py:48-110), folded tables of elg_prepare_model
+//   vps_h = W_h VPE_h       A = softmax weights of local head h over the <= 48 sequence positions (TMEM)
+//                           B = (Wv PE(p)) of head h, 16 x KT (smem, model constant)
+//   [pem | z] = ol [PW | ZW]  A = local attention output ol, 32 wide (TMEM)   B = (K1 + 4) x 32 (smem, model constant)
 //
 // Split precision (x = hi + lo, fp16 each) with the two small cross terms issued BEFORE hi*hi into the same fp32
 // accumulator keeps every contraction fp32-grade (tests/test_umma_selftest.py).
 //
 // CTA = one (aug-instance, tile of <= 112 POMO rows); TMEM lane = row.  16 warps: warp w owns TMEM lane quadrant
-// q = w % 4 (rows 32q..32q+31) and sub-slot wsub = w / 4:
+// q = w % 4 (rows 32q..32q+31) and sub-slot wsub = w / 4, so a row is served by four threads in four warps that
+// exchange data through the row's TMEM lane or through shared memory + a 128-thread named barrier:
+//   L        local policy, thread = (row, quarter wsub of the local sequence): rank-space validity bits of the
+//            distance-presorted neighbour list, first-k walk by bit scans, features from the pair table, 4-head
+//            scores + softmax weights -> TMEM A operand; the two contractions on the tensor core; thread =
+//            (row, local head wsub) in between; results to shared memory ordered by node id
 //   softmax  two independent groups of 8 warps (grp = wsub / 2): group g walks heads 4g..4g+3 one at a time through
 //            its own S/P buffer, its own mbarrier and a 256-thread named barrier, so one group's tensor-core / TMEM
 //            latency is covered by the other group's arithmetic.  thread = (row, key half kh = wsub & 1); the two
 //            halves of a row exchange (max, sum) through shared memory + a 64-thread named barrier
-//   B1       local policy, octet of lanes per row exactly as in rollout.cu (4-row tasks dealt to the groups, run
-//            while the tensor core works on P.V / the next Q.K), results to shared memory ordered by node id
 //   B3       thread = (row, quarter wsub of the node columns): clip*tanh(score + eb + {penalty+local | xi}) + mask,
 //            first-max argmax combined across the 4 quarters through shared memory
 //   C        env step: every thread of a row recomputes the scalar state, owns mask word wsub
 //
 // TMEM columns: [0,128) Q hi|lo, later O hi|lo   [128,256) O accumulators (8 heads x 16)
 //               [256,256+2*N1p) S / P buffers of the two groups, later the score accumulator
+//   during L (before the first Q K^T): [128,192) partial (sum, g) of the four sequence quarters, later [pem | z]
+//               [192,224) ol hi|lo   [224,256) head maxima + neighbour bits of the four quarters   [256,256+4*KT) local softmax weights hi|lo per head   [448,512) vps accumulators
 #include "rollout_common.cuh"
 
 namespace elg {
@@ -32,52 +41,66 @@ constexpr int TC_MT_MAX = 112;
 constexpr uint32_t TC_COL_Q = 0, TC_COL_O = 128, TC_COL_S = 256;
 constexpr float TC_P_SCALE_LOG2 = 10.f;      // softmax weights are 2^(s - m + 10): keeps small weights out of fp16 subnormals
 
-struct TcLayout {
-  int ops, eb, xy, dem, wl, u, tt, a, vpe, pw, pb, zw, zb;
-  int cur, first, load, tlen, fin, logp, mask, vis, ids, add, nb, xch, ctrl, bar;
-  int total;      // floats
+constexpr uint32_t TC_COL_PX = 128, TC_COL_D2 = 128, TC_COL_A2 = 192, TC_COL_A1 = 256, TC_COL_D1 = 448;
+constexpr int TC_XCH_FLOATS = 2 * 4 * 128 * 4;      // local-policy exchanges (validity words, neighbour bits), alias `add`
+
+// Shared-memory layout in floats.  Every offset is a compile-time constant (sized for the largest resident instance:
+// 112 node slots, 112 rows, KT local positions), so that shared-memory addresses are immediates instead of registers.
+constexpr int TC_NP = 112;                  // node slots (N1 rounded up to 16, at most)
+__host__ __device__ constexpr int tc_r4(int x) { return (x + 3) & ~3; }
+__host__ __device__ constexpr int tc_n2(int K1) { return (K1 + 4 + 15) & ~15; }      // columns of [pem | z]
+template <int KT>
+struct TcL {
+  static constexpr int MT = TC_MT_MAX;
+  static constexpr int ops = 0;                                  // E' | K' | V^T slots, each fp16 hi + lo (TC_NP x 128 x 2 x 2 bytes)
+  static constexpr int op1 = ops + 3 * TC_NP * 128;              // per local head: (Wv PE)_h^T, 16 x KT, fp16 hi + lo
+  static constexpr int op2 = op1 + LH * KT * 16;                 // [PW | ZW], (K1 + 4 -> N2) x 32, fp16 hi + lo
+  static constexpr int eb = op2 + tc_n2(KT) * LE;
+  static constexpr int xy = eb + TC_NP;
+  static constexpr int dem = xy + 2 * TC_NP;
+  static constexpr int wl = dem + TC_NP;
+  static constexpr int u = wl + E;
+  static constexpr int tt = u + LH * 4;
+  static constexpr int a = tt + LH * KT_MAX;                     // (Wv We)[c][0..2], (Wv be)[c]
+  static constexpr int pb = a + LE * 4;
+  static constexpr int zb = pb + KT_MAX;
+  static constexpr int cur = zb + 4;
+  static constexpr int first = cur + MT;
+  static constexpr int load = first + MT;
+  static constexpr int tlen = load + MT;
+  static constexpr int fin = tlen + MT;
+  static constexpr int mask = fin + MT;                           // word-major [4][128]: bank = row % 32 whatever the word
+  static constexpr int vis = mask + 4 * 128;
+  static constexpr int add = vis + MT * 4;                       // penalty + local of each row's neighbours (stride KT), ordered by node id
+  static constexpr int nb = add + (MT * KT > TC_XCH_FLOATS ? MT * KT : TC_XCH_FLOATS);   // neighbour bit mask per row
+  static constexpr int xch = nb + MT * 4;                        // softmax (max, sum) exchange; later the 4 argmax candidates per row
+  static constexpr int ctrl = xch + 2 * 4 * 128;
+  static constexpr int bar = ctrl + 4;                           // 5 mbarriers + TMEM base address
+  static constexpr int total = bar + 12;
 };
-__host__ __device__ inline int tc_r4(int x) { return (x + 3) & ~3; }
-__host__ __device__ inline TcLayout make_tc_layout(int N1, int MT, int KT, int K1) {
-  TcLayout L;
-  const int N1p = (N1 + 15) & ~15;
-  int o = 0;
-  L.ops = o; o += 3 * N1p * 128;            // E' | K' | V^T, each fp16 hi + lo (N1p x 128 x 2 x 2 bytes)
-  L.eb = o; o += N1p;
-  L.xy = o; o += 2 * N1p;
-  L.dem = o; o += N1p;
-  L.wl = o; o += E;
-  L.u = o; o += LH * 4;
-  L.tt = o; o += LH * KT_MAX;
-  L.a = o; o += LE * 4;                     // (Wv We)[c][0..2], (Wv be)[c]
-  L.vpe = o; o += KT * TS;
-  L.pw = o; o += KT * TS;
-  L.pb = o; o += KT_MAX;
-  L.zw = o; o += LE * 4;
-  L.zb = o; o += 4;
-  L.cur = o; o += MT;
-  L.first = o; o += MT;
-  L.load = o; o += MT;
-  L.tlen = o; o += MT;
-  L.fin = o; o += MT;
-  L.logp = o; o += MT;
-  L.mask = o; o += MT * 4;
-  L.vis = o; o += MT * 4;
-  L.ids = o; o += RW * 4 * (KT_MAX / 4);    // per octet: 64 uint8 neighbour ids
-  L.add = o; o += tc_r4(MT * K1);           // penalty + local of each row's neighbours, ordered by node id
-  L.nb = o; o += MT * 4;                    // neighbour bit mask per row
-  L.xch = o; o += 2 * 4 * 128;              // softmax (max, sum) exchange; later the 4 argmax candidates per row
-  L.ctrl = o; o += 4;
-  L.bar = o; o += 12;                       // 4 mbarriers + TMEM base address
-  L.total = o;
-  return L;
-}
+static_assert(TcL<48>::total * 4 <= 227 * 1024 && TcL<32>::total * 4 <= 227 * 1024, "layout exceeds one SM's shared memory");
 
 __device__ __forceinline__ uint32_t pick4(const uint32_t (&w)[4], int i) {
   return i == 0 ? w[0] : (i == 1 ? w[1] : (i == 2 ? w[2] : (i == 3 ? w[3] : 0u)));
 }
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void quad_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// position (0..127) of the n-th (0-based) set bit of the 128-bit value r[3]:r[2]:r[1]:r[0]; n < popc(r)
+__device__ __forceinline__ int select128(const uint32_t (&r)[4], int n) {
+  const int c0 = __popc(r[0]), c1 = c0 + __popc(r[1]), c2 = c1 + __popc(r[2]);
+  const int w = (n >= c0 ? 1 : 0) + (n >= c1 ? 1 : 0) + (n >= c2 ? 1 : 0);
+  int m = n - (w == 0 ? 0 : (w == 1 ? c0 : (w == 2 ? c1 : c2)));
+  uint32_t x = pick4(r, w);
+  int pos = 0, t;
+  t = __popc(x & 0xffffu); if (m >= t) { m -= t; pos = 16; x >>= 16; }
+  t = __popc(x & 0xffu);   if (m >= t) { m -= t; pos += 8; x >>= 8; }
+  t = __popc(x & 0xfu);    if (m >= t) { m -= t; pos += 4; x >>= 4; }
+  t = __popc(x & 0x3u);    if (m >= t) { m -= t; pos += 2; x >>= 2; }
+  t = (int)(x & 1u);       if (m >= t) pos += 1;
+  return w * 32 + pos;
+}
 
 // =================================================================================================
 template <int PROBLEM, int MAXE>
@@ -88,37 +111,34 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
   const int N1 = A.N1;
   const int N1p = (N1 + 15) & ~15;
   const int W = (N1 + 31) >> 5;
-  const int KT = MAXE * 8;
+  constexpr int KT = MAXE * 8;
   const int K1 = A.k_local + DEP;
-  const TcLayout L = make_tc_layout(N1, A.MT, KT, K1);
-  const float* sEb = sm + L.eb;
-  const float* sXY = sm + L.xy;
-  const float* sDem = sm + L.dem;
-  const float* sWL = sm + L.wl;
-  const float* sU = sm + L.u;
-  const float* sT = sm + L.tt;
-  const float* sA = sm + L.a;
-  const float* sVPE = sm + L.vpe;
-  const float* sPW = sm + L.pw;
-  const float* sPB = sm + L.pb;
-  const float* sZW = sm + L.zw;
-  const float* sZB = sm + L.zb;
-  int* sCur = reinterpret_cast<int*>(sm + L.cur);
-  int* sFirst = reinterpret_cast<int*>(sm + L.first);
-  float* sLoad = sm + L.load;
-  float* sTlen = sm + L.tlen;
-  int* sFin = reinterpret_cast<int*>(sm + L.fin);
-  float* sLogp = sm + L.logp;
-  uint32_t* sMask = reinterpret_cast<uint32_t*>(sm + L.mask);
-  uint32_t* sVis = reinterpret_cast<uint32_t*>(sm + L.vis);
-  float* sAdd = sm + L.add;
-  uint32_t* sNb = reinterpret_cast<uint32_t*>(sm + L.nb);
-  float* sXm = sm + L.xch;              // [4][128]
-  float* sXl = sm + L.xch + 512;        // [4][128]
-  int* sCtrl = reinterpret_cast<int*>(sm + L.ctrl);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);      // TMA completion
+  using L = TcL<MAXE * 8>;
+  const float* sEb = sm + L::eb;
+  const float* sXY = sm + L::xy;
+  const float* sDem = sm + L::dem;
+  const float* sWL = sm + L::wl;
+  const float* sU = sm + L::u;
+  const float* sT = sm + L::tt;
+  const float* sA = sm + L::a;
+  const float* sPB = sm + L::pb;
+  const float* sZB = sm + L::zb;
+  int* sCur = reinterpret_cast<int*>(sm + L::cur);
+  int* sFirst = reinterpret_cast<int*>(sm + L::first);
+  float* sLoad = sm + L::load;
+  float* sTlen = sm + L::tlen;
+  int* sFin = reinterpret_cast<int*>(sm + L::fin);
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(sm + L::mask);
+  uint32_t* sVis = reinterpret_cast<uint32_t*>(sm + L::vis);
+  float* sAdd = sm + L::add;
+  uint32_t* sNb = reinterpret_cast<uint32_t*>(sm + L::nb);
+  float* sXm = sm + L::xch;              // [4][128]
+  float* sXl = sm + L::xch + 512;        // [4][128]
+  int* sCtrl = reinterpret_cast<int*>(sm + L::ctrl);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L::bar);      // TMA completion
   uint64_t* bar_sc = bar + 1;                                     // tcgen05.commit of the score MMA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+  uint64_t* bar_loc = bar + 4;                                    // tcgen05.commit of the local-policy MMAs
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, wsub = warp >> 2, grp = wsub >> 1, kh = wsub & 1;     // softmax group (heads 4*grp..), key half
@@ -130,28 +150,29 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
   {
     const float* loc = A.derived + DER_LOC;
     float* w = sm;
-    for (int i = tid; i < E; i += RT) w[L.wl + i] = A.derived[DER_WL + i];
-    for (int i = tid; i < LH * 4; i += RT) w[L.u + i] = loc[LOC_U + i];
-    for (int i = tid; i < LH * KT_MAX; i += RT) w[L.tt + i] = loc[LOC_T + i];
-    for (int i = tid; i < LE * 4; i += RT) {
-      w[L.a + i] = (i & 3) == 3 ? loc[LOC_CV + (i >> 2)] : loc[LOC_A + i];
-      w[L.zw + i] = loc[LOC_ZW + i];
+    for (int i = tid; i < E; i += RT) w[L::wl + i] = A.derived[DER_WL + i];
+    for (int i = tid; i < LH * 4; i += RT) w[L::u + i] = loc[LOC_U + i];
+    for (int i = tid; i < LH * KT_MAX; i += RT) w[L::tt + i] = loc[LOC_T + i];
+    for (int i = tid; i < LE * 4; i += RT) w[L::a + i] = (i & 3) == 3 ? loc[LOC_CV + (i >> 2)] : loc[LOC_A + i];
+    for (int i = tid; i < KT_MAX; i += RT) w[L::pb + i] = loc[LOC_PB + i];
+    for (int i = tid; i < 4; i += RT) w[L::zb + i] = loc[LOC_ZB + i];
+    // local-policy B operands (model constants, written in the tcgen05 layout by elg_prepare_model): per head
+    // [hi | lo] of the first KT sequence positions out of KT_MAX; [PW | ZW] as built for this model's K1
+    for (int i = tid; i < LH * KT * 16; i += RT) {            // 32-bit words: per head 2 x KT * 8
+      const int h = i / (KT * 16), r = i % (KT * 16), part = r / (KT * 8), x = r % (KT * 8);
+      w[L::op1 + i] = loc[LOC_OP1 + h * (KT_MAX * 16) + part * (KT_MAX * 8) + x];
     }
-    for (int i = tid; i < KT_MAX; i += RT) w[L.pb + i] = loc[LOC_PB + i];
-    for (int i = tid; i < 4; i += RT) w[L.zb + i] = loc[LOC_ZB + i];
-    for (int i = tid; i < KT * LE; i += RT) {
-      int p = i / LE, c = i % LE;
-      w[L.vpe + p * TS + c] = loc[LOC_VPE + i];
-      w[L.pw + p * TS + c] = loc[LOC_PW + i];
-    }
+    for (int i = tid; i < tc_n2(K1) * LE; i += RT) w[L::op2 + i] = loc[LOC_OP2 + i];
     if (tid == 0) {
       mbar_init(bar, 1);
       mbar_init(bar + 1, 1);
       mbar_init(bar + 2, 1);
       mbar_init(bar + 3, 1);
+      mbar_init(bar + 4, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) umma::tmem_alloc(tmem_ptr, 512);
+    umma::fence_async_smem();
     umma::fence_before_sync();
   }
   __syncthreads();
@@ -162,16 +183,24 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
   // tensor-core operand addresses (shared memory) and instruction descriptors
   const uint32_t seg = (uint32_t)N1p * 512u;                    // bytes of one operand (hi + lo)
   const uint32_t half = (uint32_t)N1p * 256u;
-  const uint32_t opE = umma::smem_addr(sm + L.ops), opK = opE + seg, opV = opK + seg;
+  constexpr uint32_t slot = TC_NP * 512u;                      // bytes of one operand slot
+  const uint32_t opE = umma::smem_addr(sm + L::ops), opK = opE + slot, opV = opK + slot;
   const uint32_t lboN = (uint32_t)N1p * 16u;                    // K' / E': N1p rows per 8-column chunk
   const uint32_t idescS = umma::make_idesc_f16(128, N1p), idescO = umma::make_idesc_f16(128, 16);
   const int nks = N1p >> 4;
+  // local policy: thread (row, wsub) owns sequence positions [wsub * PT, wsub * PT + PT)
+  constexpr int PT = MAXE * 2;
+  const int N2 = tc_n2(K1);
+  const uint32_t op1 = umma::smem_addr(sm + L::op1), op2 = umma::smem_addr(sm + L::op2);
+  const uint32_t idescL2 = umma::make_idesc_f16(128, N2);
 
   const int total_work = A.B * A.tiles;
-  uint32_t bar_phase = 0, sc_phase = 0, grp_phase = 0;
+  // mbarrier parities: bar_loc completes twice per decode step (always 0, then 1), bar_sc once and each bar_grp five
+  // times (four rounds + the accumulated O), so both follow the parity of the number of decode steps done so far
+  uint32_t bar_phase = 0, step_par = 0;
   const bool leader = tid == grp * 256;                           // issues this group's MMAs
 #ifdef ELG_PHASE_TIMING
-  unsigned long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long pclk[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
   for (int iter = 0;; ++iter) {
@@ -193,17 +222,17 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(bar, 3 * seg);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(A.t.e) + (size_t)b * 3 * seg;
-      uint8_t* dst = reinterpret_cast<uint8_t*>(sm + L.ops);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(sm + L::ops);
       bulk_g2s(dst, src, seg, bar);
-      bulk_g2s(dst + seg, src + seg, seg, bar);
-      bulk_g2s(dst + 2 * seg, src + 2 * seg, seg, bar);
+      bulk_g2s(dst + slot, src + seg, seg, bar);
+      bulk_g2s(dst + 2 * slot, src + 2 * seg, seg, bar);
     }
     for (int i = tid; i < N1p; i += RT) {
       const bool ok = i < N1;
-      (sm + L.eb)[i] = ok ? A.t.eb[(size_t)b * N1 + i] : 0.f;
-      (sm + L.xy)[2 * i] = ok ? A.t.xy[((size_t)b * N1 + i) * 2] : 0.f;
-      (sm + L.xy)[2 * i + 1] = ok ? A.t.xy[((size_t)b * N1 + i) * 2 + 1] : 0.f;
-      (sm + L.dem)[i] = (CVRP && ok) ? A.t.demand[(size_t)b * N1 + i] : 0.f;
+      (sm + L::eb)[i] = ok ? A.t.eb[(size_t)b * N1 + i] : 0.f;
+      (sm + L::xy)[2 * i] = ok ? A.t.xy[((size_t)b * N1 + i) * 2] : 0.f;
+      (sm + L::xy)[2 * i + 1] = ok ? A.t.xy[((size_t)b * N1 + i) * 2 + 1] : 0.f;
+      (sm + L::dem)[i] = (CVRP && ok) ? A.t.demand[(size_t)b * N1 + i] : 0.f;
     }
     for (int r = tid; r < A.MT; r += RT) {
       const size_t g = (size_t)b * A.M + row0 + r;
@@ -218,18 +247,63 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         sFin[r] = ok ? 0 : 1;
       }
       sTlen[r] = 0.f;
-      sLogp[r] = 0.f;
     }
     for (int i = tid; i < A.MT * 4; i += RT) {
       const int r = i >> 2, w = i & 3;
       sVis[i] = 0u;
-      sMask[i] = (A.single_step && r < nrows && w < W) ? A.st_mask[((size_t)b * A.M + row0 + r) * W + w] : 0u;
+      sMask[w * 128 + r] = (A.single_step && r < nrows && w < W) ? A.st_mask[((size_t)b * A.M + row0 + r) * W + w] : 0u;
     }
     mbar_wait(bar, bar_phase);
     bar_phase ^= 1;
     __syncthreads();
 
     const bool in_tile = row < nrows;
+    // Start of a decode step: the row's two 16-byte chunks of the neighbour list of `cur` and its query row are fetched
+    // together; the Q operand  q = Wq_last [enc[cur]; load] (cvrp) / q_first + Wq_last enc[cur] (tsp), fp16 hi/lo -> TMEM,
+    // is finished after the list has been tested (tcgen05.st is warp-collective: every lane stores, dead rows zeros)
+    uint4 preLa = make_uint4(0, 0, 0, 0), preLb = make_uint4(0, 0, 0, 0);
+    auto prefetch_step = [&](float4 (&qv)[2 * D / 4], int cur, int first, bool live) {
+      preLa = preLb = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int d4 = 0; d4 < 2 * D / 4; ++d4) qv[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const uint4* lp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_NODE_BYTES(N1));
+        preLa = __ldg(lp + 2 * wsub);
+        preLb = __ldg(lp + 2 * wsub + 1);
+        const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur) * E + 2 * wsub * D);
+#pragma unroll
+        for (int d4 = 0; d4 < 2 * D / 4; ++d4) qv[d4] = __ldg(qp + d4);
+        if (!CVRP) {
+          const float4* fp = reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + first) * E + 2 * wsub * D);
+#pragma unroll
+          for (int d4 = 0; d4 < 2 * D / 4; ++d4) {
+            const float4 f4 = __ldg(fp + d4);
+            qv[d4].x = f4.x + qv[d4].x; qv[d4].y = f4.y + qv[d4].y; qv[d4].z = f4.z + qv[d4].z; qv[d4].w = f4.w + qv[d4].w;
+          }
+        }
+      }
+    };
+    auto finish_step = [&](const float4 (&qv)[2 * D / 4], float ld, bool live) {
+      uint32_t hw[16], lw[16];
+      if (live) {
+#pragma unroll
+        for (int d4 = 0; d4 < 2 * D / 4; ++d4) {
+          float4 v4 = qv[d4];
+          if (CVRP) {
+            const float4 wl = *reinterpret_cast<const float4*>(sWL + 2 * wsub * D + d4 * 4);
+            v4.x = fmaf(ld, wl.x, v4.x); v4.y = fmaf(ld, wl.y, v4.y);
+            v4.z = fmaf(ld, wl.z, v4.z); v4.w = fmaf(ld, wl.w, v4.w);
+          }
+          umma::split2_f16(v4.x, v4.y, hw[d4 * 2], lw[d4 * 2]);
+          umma::split2_f16(v4.z, v4.w, hw[d4 * 2 + 1], lw[d4 * 2 + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hw[i] = lw[i] = 0u;
+      }
+      umma::st16s<1>(tl + TC_COL_Q + 16 * wsub, hw);
+      umma::st16s<1>(tl + TC_COL_Q + 64 + 16 * wsub, lw);
+    };
     int t = 0;
     for (;; ++t) {
       const bool forced = !A.single_step && (t < 1 + DEP);
@@ -240,50 +314,271 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
       const bool act = in_tile && !sFin[rc];
 
       if (!forced) {
-        // ---- valid-key bits of this row: unmasked and < N1 ----------------------------------------------
-        uint32_t inv[4];
+        uint32_t mw[4];
         {
-          const uint4 m4 = *reinterpret_cast<const uint4*>(sMask + rc * 4);
-          const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+          mw[0] = sMask[rc]; mw[1] = sMask[128 + rc]; mw[2] = sMask[256 + rc]; mw[3] = sMask[384 + rc];
+        }
+        float4 qv[2 * D / 4];                        // heads 2*wsub, 2*wsub + 1 of the query row: 32 consecutive k
+        prefetch_step(qv, cur0, CVRP ? 0 : sFirst[rc], act);       // global loads in flight while the list is tested
+        // =================== L: local policy (CVRP/models.py:51-175, TSP/models.py:48-110) ======================
+        // (1) validity of the distance-presorted neighbour list of `cur` in RANK space: this thread tests the 32
+        //     list entries of its two 16-byte chunks (entry e = s + 8 i sits at byte i of chunk s, nbr_pos()); the
+        //     four quarters are OR-ed through shared memory
+        const uint8_t* nrow = reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur0) * ELG_NBR_NODE_BYTES(N1);
+        uint32_t R[4];
+        {
+          uint32_t rp[4] = {0u, 0u, 0u, 0u};
+          if (act) {
+            const uint32_t lw2[2][4] = {{preLa.x, preLa.y, preLa.z, preLa.w}, {preLb.x, preLb.y, preLb.z, preLb.w}};
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t id = (lw2[c][i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                const uint32_t free1 = ~__funnelshift_r(sMask[(id >> 5) * 128 + rc], 0u, id) & 1u;      // conflict-free: bank = row % 32
+                rp[i >> 2] |= free1 << ((i & 3) * 8 + c);
+              }
+          }
+          uint4* xr = reinterpret_cast<uint4*>(sAdd);                     // [4][128] exchange (aliases the dead `add` rows)
+          xr[wsub * 128 + row] = make_uint4(rp[0] << (2 * wsub), rp[1] << (2 * wsub), rp[2] << (2 * wsub), rp[3] << (2 * wsub));
+          quad_sync(11 + q);
+          const uint4 x0 = xr[row], x1 = xr[128 + row], x2 = xr[256 + row], x3 = xr[384 + row];
+          R[0] = x0.x | x1.x | x2.x | x3.x; R[1] = x0.y | x1.y | x2.y | x3.y;
+          R[2] = x0.z | x1.z | x2.z | x3.z; R[3] = x0.w | x1.w | x2.w | x3.w;
+          const int NLs = N1 - DEP;                                        // list entries; the padding holds id 0
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const int nb = N1 - w * 32;
-            const uint32_t lim = nb >= 32 ? FULL : (nb > 0 ? ((1u << nb) - 1u) : 0u);
-            inv[w] = act ? (~mw[w] & lim) : 0u;
+            const int nb = NLs - w * 32;
+            R[w] &= nb >= 32 ? FULL : (nb > 0 ? ((1u << nb) - 1u) : 0u);
           }
         }
-        // ---- Q operand: q = Wq_last [enc[cur]; load] (cvrp) / q_first + Wq_last enc[cur] (tsp), fp16 hi/lo -> TMEM ----
+        finish_step(qv, ld0, act);
+        PHASE_MARK(0);
+        const bool depot_masked = (mw[0] & 1u) != 0u;
+        // (2) the first kk = min(k, #valid) set bits are the local neighbourhood, in rank order; with the depot in
+        //     front (cvrp) they are sequence positions p = 0 .. np-1; this thread owns p in [wsub PT, wsub PT + PT)
+        const int kk = min(__popc(R[0]) + __popc(R[1]) + __popc(R[2]) + __popc(R[3]), A.k_local);
+        const int np = act ? kk + DEP : 0;
+        const int p0 = wsub * PT;
+        const float4* rec = reinterpret_cast<const float4*>(nrow + ELG_NBR_STRIDE + ELG_NBR_PAIR_BYTES(N1));   // by list rank
+        float f0[PT], f1[PT], f2[PT];
+        float cpen = 1.f;                                                 // distance penalty = -f0 * cpen
+        uint32_t idw[PT / 4];                                             // this thread's node ids, 4 per word
+        uint32_t nbp[4] = {0u, 0u, 0u, 0u};                               // their bits in node space
         {
-          uint32_t hw[16], lw[16];                     // heads 2*wsub, 2*wsub + 1: 32 consecutive k
-          if (act) {
-            const float4* qp = reinterpret_cast<const float4*>(A.t.qtab + ((size_t)b * N1 + cur0) * E + 2 * wsub * D);
-            const float4* fp = CVRP ? nullptr : reinterpret_cast<const float4*>(A.t.qfirst + ((size_t)b * N1 + sFirst[rc]) * E + 2 * wsub * D);
-#pragma unroll
-            for (int d4 = 0; d4 < 2 * D / 4; ++d4) {
-              float4 v4 = __ldg(qp + d4);
-              if (CVRP) {
-                const float4 wl = *reinterpret_cast<const float4*>(sWL + 2 * wsub * D + d4 * 4);
-                v4.x = fmaf(ld0, wl.x, v4.x); v4.y = fmaf(ld0, wl.y, v4.y);
-                v4.z = fmaf(ld0, wl.z, v4.z); v4.w = fmaf(ld0, wl.w, v4.w);
-              } else {
-                const float4 f4 = __ldg(fp + d4);
-                v4.x = f4.x + v4.x; v4.y = f4.y + v4.y; v4.z = f4.z + v4.z; v4.w = f4.w + v4.w;
-              }
-              umma::split2_f16(v4.x, v4.y, hw[d4 * 2], lw[d4 * 2]);
-              umma::split2_f16(v4.z, v4.w, hw[d4 * 2 + 1], lw[d4 * 2 + 1]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) hw[i] = lw[i] = 0u;
+          // list positions of my neighbours: skip to the first one with a rank select, then walk the set bits
+          int epos[PT];
+          unsigned long long ra = 0ull, rb = 0ull;
+          const int cfirst = max(p0 - DEP, 0);                            // rank of my first neighbour among the valid ones
+          if (cfirst < kk) {
+            const int e0 = select128(R, cfirst);
+            ra = ((unsigned long long)R[1] << 32) | R[0];
+            rb = ((unsigned long long)R[3] << 32) | R[2];
+            if (e0 < 64) { ra &= ~0ull << e0; } else { ra = 0ull; rb &= ~0ull << (e0 - 64); }
           }
-          umma::st16s<1>(tl + TC_COL_Q + 16 * wsub, hw);
-          umma::st16s<1>(tl + TC_COL_Q + 64 + 16 * wsub, lw);
+#pragma unroll
+          for (int s = 0; s < PT; ++s) {
+            epos[s] = 0;
+            if (DEP && s == 0 && wsub == 0) continue;                     // the depot: features (0, 0, 0), node 0
+            const bool in_a = ra != 0ull;
+            const unsigned long long x = in_a ? ra : rb;
+            epos[s] = max(__ffsll((long long)x) - 1, 0) + (in_a ? 0 : 64);
+            const unsigned long long y = x & (x - 1ull);
+            ra = in_a ? y : ra;
+            rb = in_a ? rb : y;
+          }
+          // one 16-byte record per neighbour: (distance, angle, demand, node id); the largest distance is the last one's
+          float4 rv[PT];
+          float4 rlast = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kk > 0) rlast = __ldg(rec + select128(R, kk - 1));
+#pragma unroll
+          for (int s = 0; s < PT; ++s) {
+            const bool mine = (p0 + s) < np && !(DEP && s == 0 && wsub == 0);
+            rv[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mine) rv[s] = __ldg(rec + epos[s]);
+          }
+          const float dmax = rlast.x;
+          const float r0d = dmax != 0.f ? 1.f / (dmax + 1e-6f) : 1.f;      // cvrp: cur_dist / (max + 1e-6); dmax == 0 -> dd itself
+          // penalty -d / dmax (no eps, CVRP/models.py:380,403) = -f0 (dmax + 1e-6) / dmax; tsp: -d / (dmax + 1e-6) = -f0
+          if (CVRP && dmax != 0.f) cpen = (dmax + 1e-6f) / dmax;
+          const float rtsp = 1.f / (dmax + 1e-6f);
+          const float rld = 1.f / ld0;
+#pragma unroll
+          for (int i = 0; i < PT / 4; ++i) idw[i] = 0u;
+          unsigned long long na = 0ull, nb2 = 0ull;
+#pragma unroll
+          for (int s = 0; s < PT; ++s) {
+            const bool mine = (p0 + s) < np && !(DEP && s == 0 && wsub == 0);
+            f0[s] = f1[s] = f2[s] = 0.f;
+            if (mine) {
+              const int nd = __float_as_int(rv[s].w);
+              idw[s >> 2] |= (uint32_t)nd << ((s & 3) * 8);
+              if (CVRP) {
+                f0[s] = rv[s].x * r0d;
+                f2[s] = rv[s].z * rld;
+              } else {
+                f0[s] = rv[s].x * rtsp;
+              }
+              f1[s] = rv[s].y;
+              const unsigned long long bit = 1ull << (nd & 63);
+              na |= (nd & 64) ? 0ull : bit;
+              nb2 |= (nd & 64) ? bit : 0ull;
+            }
+          }
+          if (DEP && wsub == 0 && np > 0) na |= 1ull;                     // the depot heads the local sequence
+          nbp[0] = (uint32_t)na; nbp[1] = (uint32_t)(na >> 32); nbp[2] = (uint32_t)nb2; nbp[3] = (uint32_t)(nb2 >> 32);
+        }
+        PHASE_MARK(1);
+        // (3) scores of the constant local query, all four heads for my positions (log2 domain); the row's maximum
+        //     per head and the neighbour bits of the row come from the four quarters through shared memory
+        // score of position s under head h given the head's (u0, u1, u2) and table entries t[s]; positions past np and a
+        // masked depot (standing on it) score -inf
+        const int nv = np - p0;                                           // my valid positions are s < nv
+        const bool dep_off = DEP && wsub == 0 && depot_masked;
+        auto load_head = [&](int h, float4& u, float (&tq)[PT]) {
+          u = *reinterpret_cast<const float4*>(sU + h * 4);
+#pragma unroll
+          for (int i = 0; i < PT / 4; ++i) {
+            const float4 t4 = *reinterpret_cast<const float4*>(sT + h * KT_MAX + p0 + 4 * i);
+            tq[4 * i] = t4.x; tq[4 * i + 1] = t4.y; tq[4 * i + 2] = t4.z; tq[4 * i + 3] = t4.w;
+          }
+          if (dep_off) tq[0] = -INFINITY;
+        };
+        auto lscore = [&](const float4& u, const float (&tq)[PT], int s) -> float {
+          const float v = fmaf(u.z, f2[s], fmaf(u.y, f1[s], fmaf(u.x, f0[s], tq[s])));
+          return s < nv ? v : -INFINITY;
+        };
+        float mh[LH];
+        {
+          uint32_t nbw[4];                                                // neighbour bit mask of the row (node space)
+          // the maxima only serve as a common offset: rounded UP to fp16 they fit 8 bytes per thread (softmax exchange area)
+          uint32_t mp[2];
+          {
+            float m4[LH];
+#pragma unroll
+            for (int h = 0; h < LH; ++h) {
+              float4 u;
+              float tq[PT];
+              load_head(h, u, tq);
+              float m = -INFINITY;
+#pragma unroll
+              for (int s = 0; s < PT; ++s) m = fmaxf(m, lscore(u, tq, s));
+              m4[h] = m;
+            }
+            mp[0] = umma::pack_h2(__float2half_ru(m4[0]), __float2half_ru(m4[1]));
+            mp[1] = umma::pack_h2(__float2half_ru(m4[2]), __float2half_ru(m4[3]));
+          }
+          uint2* xm = reinterpret_cast<uint2*>(sXm);                      // [4][128]
+          uint4* xn = reinterpret_cast<uint4*>(sAdd) + 512;               // [4][128], behind the validity exchange
+          xm[wsub * 128 + row] = make_uint2(mp[0], mp[1]);
+          xn[wsub * 128 + row] = make_uint4(nbp[0], nbp[1], nbp[2], nbp[3]);
+          quad_sync(11 + q);
+          {
+            const uint2 a0 = xm[row], a1 = xm[128 + row], a2 = xm[256 + row], a3 = xm[384 + row];
+            const __half2 h01 = __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&a0.x), *reinterpret_cast<const __half2*>(&a1.x)),
+                                        __hmax2(*reinterpret_cast<const __half2*>(&a2.x), *reinterpret_cast<const __half2*>(&a3.x)));
+            const __half2 h23 = __hmax2(__hmax2(*reinterpret_cast<const __half2*>(&a0.y), *reinterpret_cast<const __half2*>(&a1.y)),
+                                        __hmax2(*reinterpret_cast<const __half2*>(&a2.y), *reinterpret_cast<const __half2*>(&a3.y)));
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            mh[0] = f01.x; mh[1] = f01.y; mh[2] = f23.x; mh[3] = f23.y;
+            const uint4 n0 = xn[row], n1 = xn[128 + row], n2 = xn[256 + row], n3 = xn[384 + row];
+            nbw[0] = (n0.x | n1.x) | (n2.x | n3.x); nbw[1] = (n0.y | n1.y) | (n2.y | n3.y);
+            nbw[2] = (n0.z | n1.z) | (n2.z | n3.z); nbw[3] = (n0.w | n1.w) | (n2.w | n3.w);
+          }
+          if (wsub == 0 && act) *reinterpret_cast<uint4*>(sNb + rc * 4) = make_uint4(nbw[0], nbw[1], nbw[2], nbw[3]);   // read back in (6) and B3
+        }
+        PHASE_MARK(2);
+        // (4) weights 2^(s - max + 10) -> A operand of head h (TMEM, fp16 hi/lo, slot = sequence position); partial
+        //     (sum, sum w f) of my positions -> TMEM exchange columns
+        {
+#pragma unroll
+          for (int h = 0; h < LH; ++h) {
+            const float moff = mh[h] == -INFINITY ? 0.f : mh[h] - TC_P_SCALE_LOG2;
+            float sum = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            uint32_t hw[PT / 2], lw[PT / 2];
+            float4 u;
+            float tq[PT];
+            load_head(h, u, tq);
+#pragma unroll
+            for (int i = 0; i < PT / 2; ++i) {
+              const float w0 = umma::ex2_raw(lscore(u, tq, 2 * i) - moff); // -inf (masked / beyond np) -> 0
+              const float w1 = umma::ex2_raw(lscore(u, tq, 2 * i + 1) - moff);
+              sum += w0;
+              g0 = fmaf(w0, f0[2 * i], g0); g1 = fmaf(w0, f1[2 * i], g1); g2 = fmaf(w0, f2[2 * i], g2);
+              sum += w1;
+              g0 = fmaf(w1, f0[2 * i + 1], g0); g1 = fmaf(w1, f1[2 * i + 1], g1); g2 = fmaf(w1, f2[2 * i + 1], g2);
+              umma::split2_f16(w0, w1, hw[i], lw[i]);
+            }
+            const uint32_t ca = tl + TC_COL_A1 + h * KT + wsub * (PT / 2);
+            if (PT == 8) {
+              umma::st4(ca, hw);
+              umma::st4(ca + KT / 2, lw);
+            } else {                                                       // PT == 12
+              umma::st4(ca, hw); umma::st2(ca + 4, hw + 4);
+              umma::st4(ca + KT / 2, lw); umma::st2(ca + KT / 2 + 4, lw + 4);
+            }
+            const uint32_t px[4] = {__float_as_uint(sum), __float_as_uint(g0), __float_as_uint(g1), __float_as_uint(g2)};
+            umma::st4(tl + TC_COL_PX + 16 * wsub + 4 * h, px);
+          }
+        }
+        umma::wait_st();                                                   // also the Q operand
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          // vps_h = W_h (Wv PE)_h: per head KT/16 k-steps x (lo*hi, hi*lo, hi*hi)
+          umma::fence_after_sync();
+#pragma unroll
+          for (int h = 0; h < LH; ++h) {
+            const uint32_t d = tm + TC_COL_D1 + 16 * h;
+            const uint32_t aHi = tm + TC_COL_A1 + h * KT, aLo = aHi + KT / 2;
+            const uint32_t bHi = op1 + h * (KT * 64), bLo = bHi + KT * 32;
+#pragma unroll
+            for (int ks = 0; ks < KT / 16; ++ks)
+              umma::mma_f16_ts(d, aLo + 8 * ks, umma::make_desc(bHi + ks * 512, 256, 128), idescO, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < KT / 16; ++ks)
+              umma::mma_f16_ts(d, aHi + 8 * ks, umma::make_desc(bLo + ks * 512, 256, 128), idescO, true);
+#pragma unroll
+            for (int ks = 0; ks < KT / 16; ++ks)
+              umma::mma_f16_ts(d, aHi + 8 * ks, umma::make_desc(bHi + ks * 512, 256, 128), idescO, true);
+          }
+          umma::commit(bar_loc);
+        }
+        PHASE_MARK(3);
+        // (5) thread = (row, local head wsub): ol = (Wv We) g + Wv be + vps, normalised -> A operand of the second
+        //     contraction
+        mbar_wait(bar_loc, 0u);
+        umma::fence_after_sync();
+        {
+          uint32_t dv[8], pq[16];
+          umma::ld8_nw(tl + TC_COL_D1 + 16 * wsub, dv);
+          umma::ld4_nw(tl + TC_COL_PX + 4 * wsub, pq);
+          umma::ld4_nw(tl + TC_COL_PX + 16 + 4 * wsub, pq + 4);
+          umma::ld4_nw(tl + TC_COL_PX + 32 + 4 * wsub, pq + 8);
+          umma::ld4_nw(tl + TC_COL_PX + 48 + 4 * wsub, pq + 12);
+          umma::wait_ld();
+          const float sum = (umma::after_wait(pq[0]) + umma::after_wait(pq[4])) + (umma::after_wait(pq[8]) + umma::after_wait(pq[12]));
+          const float inv_s = sum > 0.f ? 1.f / sum : 0.f;
+          const float g0 = ((umma::after_wait(pq[1]) + umma::after_wait(pq[5])) + (umma::after_wait(pq[9]) + umma::after_wait(pq[13]))) * inv_s;
+          const float g1 = ((umma::after_wait(pq[2]) + umma::after_wait(pq[6])) + (umma::after_wait(pq[10]) + umma::after_wait(pq[14]))) * inv_s;
+          const float g2 = ((umma::after_wait(pq[3]) + umma::after_wait(pq[7])) + (umma::after_wait(pq[11]) + umma::after_wait(pq[15]))) * inv_s;
+          float ol[LD];
+#pragma unroll
+          for (int c = 0; c < LD; ++c) {
+            const float4 a4 = *reinterpret_cast<const float4*>(sA + (wsub * LD + c) * 4);
+            ol[c] = fmaf(a4.z, g2, fmaf(a4.y, g1, a4.x * g0)) + a4.w + umma::after_wait(dv[c]) * inv_s;
+          }
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) umma::split2_f16(ol[2 * i], ol[2 * i + 1], hw[i], lw[i]);
+          umma::st4(tl + TC_COL_A2 + 4 * wsub, hw);
+          umma::st4(tl + TC_COL_A2 + 16 + 4 * wsub, lw);
         }
         umma::wait_st();
         umma::fence_before_sync();
         __syncthreads();
 
-        // MMA issue helpers (thread 0 only).  Per contraction: lo*hi, hi*lo, then hi*hi into one accumulator.
+        // MMA issue helpers (leaders only).  Per contraction: lo*hi, hi*lo, then hi*hi into one accumulator.
         auto issue_qk = [&](int head) {
           const uint32_t d = tm + TC_COL_S + grp * N1p;
           const uint32_t aHi = tm + TC_COL_Q + 8 * head, aLo = aHi + 64;
@@ -306,12 +601,72 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         };
         if (leader) {
           umma::fence_after_sync();
+          if (tid == 0) {
+            // [pem | z] = ol [PW | ZW]: 2 k-steps x (lo*hi, hi*lo, hi*hi); the accumulator takes over the exchange columns
+            const uint32_t d = tm + TC_COL_D2, aHi = tm + TC_COL_A2, aLo = aHi + 16;
+            const uint32_t lbo2 = (uint32_t)N2 * 16u, lo2 = (uint32_t)N2 * 64u;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma::mma_f16_ts(d, aLo + 8 * ks, umma::make_desc(op2 + ks * 2 * lbo2, lbo2, 128), idescL2, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma::mma_f16_ts(d, aHi + 8 * ks, umma::make_desc(op2 + lo2 + ks * 2 * lbo2, lbo2, 128), idescL2, true);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma::mma_f16_ts(d, aHi + 8 * ks, umma::make_desc(op2 + ks * 2 * lbo2, lbo2, 128), idescL2, true);
+            umma::commit(bar_loc);
+          }
           issue_qk(4 * grp);
           umma::commit(bar_grp);
         }
-        PHASE_MARK(0);
+        PHASE_MARK(4);
+        // (6) penalty + local score of my positions: pen + f . z + z3 + pem[p] (tables carry the 1/sqrt(32)), stored
+        //     ordered by node id for phase B3 (runs while the tensor core works on the first Q K^T)
+        mbar_wait(bar_loc, 1u);
+        umma::fence_after_sync();
+        {
+          uint32_t dp[PT], dz[4];
+          if (PT == 8) {
+            umma::ld8_nw(tl + TC_COL_D2 + p0, dp);
+          } else {
+            umma::ld8_nw(tl + TC_COL_D2 + p0, dp);
+            umma::ld4_nw(tl + TC_COL_D2 + p0 + 8, dp + 8);
+          }
+          umma::ld4_nw(tl + TC_COL_D2 + K1, dz);
+          umma::wait_ld();
+          if (act) {
+            const float z0 = umma::after_wait(dz[0]) + sZB[0], z1 = umma::after_wait(dz[1]) + sZB[1];
+            const float z2 = umma::after_wait(dz[2]) + sZB[2], c0 = umma::after_wait(dz[3]) + sZB[3];
+            const uint4 n4 = *reinterpret_cast<const uint4*>(sNb + rc * 4);
+            const uint32_t nbw[4] = {n4.x, n4.y, n4.z, n4.w};
+            const int pc1 = __popc(nbw[0]), pc2 = pc1 + __popc(nbw[1]), pc3 = pc2 + __popc(nbw[2]);
+#pragma unroll
+            for (int s = 0; s < PT; ++s) {
+              const int p = p0 + s;
+              if (p < np) {
+                const float pem = umma::after_wait(dp[s]) + sPB[p];
+                const float addv = (fmaf(f2[s], z2, fmaf(f1[s], z1, f0[s] * z0)) + c0 + pem) - f0[s] * cpen;
+                const int nd = (idw[s >> 2] >> ((s & 3) * 8)) & 0xff, wd = nd >> 5;
+                const uint32_t below = pick4(nbw, wd) & ((1u << (nd & 31)) - 1u);
+                const int rank = (wd == 0 ? 0 : (wd == 1 ? pc1 : (wd == 2 ? pc2 : pc3))) + __popc(below);
+                sAdd[rc * KT + rank] = addv;
+              }
+            }
+          }
+        }
+        PHASE_MARK(5);
 
-        // this thread's window of valid-key bits: keys [kh*KH, kh*KH + KH)
+        // ---- valid-key bits of this row (unmasked and < N1); this thread's window: keys [kh*KH, kh*KH + KH) ----
+        uint32_t inv[4];
+        {
+          const uint32_t mq[4] = {sMask[rc], sMask[128 + rc], sMask[256 + rc], sMask[384 + rc]};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int nb = N1 - w * 32;
+            const uint32_t lim = nb >= 32 ? FULL : (nb > 0 ? ((1u << nb) - 1u) : 0u);
+            inv[w] = act ? (~mq[w] & lim) : 0u;
+          }
+        }
         uint32_t v0, v1;
         {
           const int s0 = kh * KH, wd = s0 >> 5, sh = s0 & 31;
@@ -322,8 +677,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
 
 #pragma unroll 1
         for (int rho = 0; rho < 4; ++rho) {
-          mbar_wait(bar_grp, grp_phase);
-          grp_phase ^= 1;
+          mbar_wait(bar_grp, (step_par + rho) & 1u);
           umma::fence_after_sync();
           const uint32_t sb = tl + TC_COL_S + grp * N1p;
           uint32_t sr[56];
@@ -387,234 +741,21 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           umma::st_words<2>(sb + (N1p >> 1) + kh * (KH >> 1), sr + 1, KH >> 1);
           umma::wait_st();
           umma::fence_before_sync();
-          group_sync(9 + grp);
+          // round 0 is CTA-wide: the first P V overwrites accumulator columns that held [pem | z], which the other
+          // group's threads may still be reading in (6)
+          if (rho == 0) __syncthreads(); else group_sync(9 + grp);
           if (leader) {
             umma::fence_after_sync();
             issue_pv(4 * grp + rho);
             if (rho < 3) issue_qk(4 * grp + rho + 1);
             umma::commit(bar_grp);
           }
-          PHASE_MARK(1);
+          PHASE_MARK(6);
 
-          // ---- B1: local policy for rows [64 rho, 64 rho + 64), octet of lanes per row, while the tensor core runs ----
-          if (rho < 2) {
-            // 4-row tasks dealt alternately to the two groups so both carry the same local-policy load
-            const int r0 = 4 * (((rho * 8 + kh * 4 + q) << 1) + grp);
-            const bool own = r0 < nrows;
-            const int rq = lane >> 3, s8 = lane & 7;
-            const int myr = own ? min(r0 + rq, nrows - 1) : 0;
-            const bool row_ok = own && (r0 + rq) < nrows;
-            const bool rlive = row_ok && !sFin[myr];
-            if (own && __any_sync(FULL, rlive)) {
-              float addv[MAXE];
-              int node[MAXE];
-              uint8_t* ids = reinterpret_cast<uint8_t*>(sm + L.ids) + (warp * 4 + rq) * KT_MAX;
-              const int cur = sCur[myr];
-              const float ldv = sLoad[myr];
-              const int NL = N1 - DEP, kloc = A.k_local;
-              const uint32_t* mrow = sMask + myr * 4;
-              const uint8_t* nrow = reinterpret_cast<const uint8_t*>(A.t.nbr) + ((size_t)b * N1 + cur) * ELG_NBR_NODE_BYTES(N1);
-              const float2* feat = reinterpret_cast<const float2*>(nrow + ELG_NBR_STRIDE);      // (distance, angle) from cur
-              int cnt = 0;
-              {
-                uint4 Lw = make_uint4(0, 0, 0, 0);
-                if (rlive) Lw = __ldg(reinterpret_cast<const uint4*>(nrow) + s8);
-                const int iters = (NL + 7) >> 3;
-#pragma unroll
-                for (int it = 0; it < 16; ++it) {
-                  if (it >= iters) break;
-                  const uint32_t wsel = it < 4 ? Lw.x : (it < 8 ? Lw.y : (it < 12 ? Lw.z : Lw.w));
-                  const int id = (wsel >> ((it & 3) * 8)) & 0xff;
-                  const int e = it * 8 + s8;
-                  const bool valid = rlive && e < NL && cnt < kloc && !((mrow[id >> 5] >> (id & 31)) & 1u);
-                  const uint32_t bal = __ballot_sync(FULL, valid);
-                  const uint32_t mine = (bal >> (lane & 24)) & 0xffu;
-                  const int rank = cnt + __popc(mine & ((1u << s8) - 1u));
-                  if (valid && rank < kloc) ids[rank] = (uint8_t)id;
-                  cnt += __popc(mine);
-                  if (__all_sync(FULL, !rlive || cnt >= kloc)) break;
-                }
-              }
-              const int kk = min(cnt, kloc);
-              const int np = rlive ? kk + DEP : 0;
-              __syncwarp();
-              // features of this lane's entries: gathered from the per-instance pair table (same dist2 / atan2f values the
-              // kernel used to recompute); the three divisions become one reciprocal each per row
-              float2 ft[MAXE];
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                node[e] = 0;
-                ft[e] = make_float2(0.f, 0.f);
-                if (p < np && !(DEP && p == 0)) {
-                  node[e] = ids[p - DEP];
-                  ft[e] = __ldg(feat + node[e]);
-                }
-              }
-              float dmax = 0.f;
-              if (kk > 0) dmax = __ldg(feat + ids[kk - 1]).x;
-              const float r0d = dmax != 0.f ? 1.f / (dmax + 1e-6f) : 1.f;      // cvrp: cur_dist / (max + 1e-6); dmax == 0 -> dd itself
-              const float r1d = dmax != 0.f ? 1.f / dmax : 1.f;                 // penalty -d / dmax (no eps, CVRP/models.py:380,403)
-              const float rtsp = 1.f / (dmax + 1e-6f);
-              const float rld = 1.f / ldv;
-              float f0[MAXE], f1[MAXE], f2[MAXE];
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                f0[e] = f1[e] = f2[e] = addv[e] = 0.f;
-                if (p < np && !(DEP && p == 0)) {
-                  const float dd = ft[e].x;
-                  if (CVRP) {
-                    f0[e] = dd * r0d;
-                    addv[e] = -(dd * r1d);
-                    f2[e] = sDem[node[e]] * rld;
-                  } else {
-                    f0[e] = dd * rtsp;
-                    addv[e] = -f0[e];
-                  }
-                  f1[e] = ft[e].y;
-                }
-              }
-              // 4-head attention of the constant query over the local sequence.  Per head the octet reduces
-              // (sum, g0..2) to every lane and the 8 value columns reduce-scatter, so lane d ends up owning ol[h*8 + d].
-              float olh[LH];
-#pragma unroll
-              for (int h = 0; h < LH; ++h) {
-                const float u0 = sU[h * 4], u1 = sU[h * 4 + 1], u2 = sU[h * 4 + 2];
-                float sc[MAXE];
-                float mx = -INFINITY;
-#pragma unroll
-                for (int e = 0; e < MAXE; ++e) {
-                  const int p = s8 + 8 * e;
-                  float v = -INFINITY;
-                  if (p < np) {
-                    v = fmaf(u2, f2[e], fmaf(u1, f1[e], u0 * f0[e])) + sT[h * KT_MAX + p];
-                    if (DEP && p == 0 && (mrow[0] & 1u)) v = -INFINITY;
-                  }
-                  sc[e] = v;
-                  mx = fmaxf(mx, v);
-                }
-                mx = octet_max(mx);
-                const float mref = mx == -INFINITY ? 0.f : mx;
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f, sum = 0.f;
-                float vp8[LD];
-#pragma unroll
-                for (int d = 0; d < LD; ++d) vp8[d] = 0.f;
-#pragma unroll
-                for (int e = 0; e < MAXE; ++e) {
-                  const int p = s8 + 8 * e;
-                  const float w = umma::ex2_raw(sc[e] - mref);          // -inf (masked / beyond np) -> 0
-                  sum += w;
-                  g0 = fmaf(w, f0[e], g0); g1 = fmaf(w, f1[e], g1); g2 = fmaf(w, f2[e], g2);
-                  if (p < np) {
-                    const float4 va = *reinterpret_cast<const float4*>(sVPE + p * TS + h * LD);
-                    const float4 vb = *reinterpret_cast<const float4*>(sVPE + p * TS + h * LD + 4);
-                    vp8[0] = fmaf(w, va.x, vp8[0]); vp8[1] = fmaf(w, va.y, vp8[1]);
-                    vp8[2] = fmaf(w, va.z, vp8[2]); vp8[3] = fmaf(w, va.w, vp8[3]);
-                    vp8[4] = fmaf(w, vb.x, vp8[4]); vp8[5] = fmaf(w, vb.y, vp8[5]);
-                    vp8[6] = fmaf(w, vb.z, vp8[6]); vp8[7] = fmaf(w, vb.w, vp8[7]);
-                  }
-                }
-                sum = octet_sum(sum);
-                const float inv_s = sum > 0.f ? 1.f / sum : 0.f;
-                g0 = octet_sum(g0) * inv_s; g1 = octet_sum(g1) * inv_s; g2 = octet_sum(g2) * inv_s;
-                // reduce-scatter of vp8 over the octet: after three exchange steps lane s8 holds the total of vp8[s8]
-                float r4[4], r2[2];
-                {
-                  const bool up = (s8 & 4) != 0;
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float send = up ? vp8[i] : vp8[i + 4];
-                    const float keep = up ? vp8[i + 4] : vp8[i];
-                    r4[i] = keep + __shfl_xor_sync(FULL, send, 4);
-                  }
-                }
-                {
-                  const bool up = (s8 & 2) != 0;
-#pragma unroll
-                  for (int i = 0; i < 2; ++i) {
-                    const float send = up ? r4[i] : r4[i + 2];
-                    const float keep = up ? r4[i + 2] : r4[i];
-                    r2[i] = keep + __shfl_xor_sync(FULL, send, 2);
-                  }
-                }
-                const bool up1 = (s8 & 1) != 0;
-                const float vps = ((up1 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, up1 ? r2[0] : r2[1], 1)) * inv_s;
-                // ol[c] = (Wv We)[c] . g + (Wv be)[c] + sum_p w_p (Wv PE(p))[c],  c = h*8 + s8
-                const float4 a4 = *reinterpret_cast<const float4*>(sA + (h * LD + s8) * 4);
-                olh[h] = fmaf(a4.z, g2, fmaf(a4.y, g1, a4.x * g0)) + a4.w + vps;
-              }
-              // z = ZW^T ol + ZB (3 feature weights + constant), partial over this lane's four ol, then octet sum
-              float z0 = 0.f, z1 = 0.f, z2 = 0.f, c0 = 0.f;
-#pragma unroll
-              for (int h = 0; h < LH; ++h) {
-                const float4 zw = *reinterpret_cast<const float4*>(sZW + (h * LD + s8) * 4);
-                z0 = fmaf(zw.x, olh[h], z0); z1 = fmaf(zw.y, olh[h], z1);
-                z2 = fmaf(zw.z, olh[h], z2); c0 = fmaf(zw.w, olh[h], c0);
-              }
-              z0 = octet_sum(z0) + sZB[0]; z1 = octet_sum(z1) + sZB[1]; z2 = octet_sum(z2) + sZB[2]; c0 = octet_sum(c0) + sZB[3];
-              // positional part PW[p] . ol of this lane's entries: ol broadcast four columns at a time
-              float pem[MAXE];
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) pem[e] = sPB[min(s8 + 8 * e, KT - 1)];
-#pragma unroll
-              for (int h = 0; h < LH; ++h) {
-#pragma unroll
-                for (int dq = 0; dq < 2; ++dq) {
-                  const float o0 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 0));
-                  const float o1 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 1));
-                  const float o2 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 2));
-                  const float o3 = __shfl_sync(FULL, olh[h], (lane & 24) | (dq * 4 + 3));
-#pragma unroll
-                  for (int e = 0; e < MAXE; ++e) {
-                    const int p = min(s8 + 8 * e, KT - 1);
-                    const float4 pw = *reinterpret_cast<const float4*>(sPW + p * TS + h * LD + dq * 4);
-                    pem[e] = fmaf(pw.w, o3, fmaf(pw.z, o2, fmaf(pw.y, o1, fmaf(pw.x, o0, pem[e]))));
-                  }
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e)      // penalty + local score (tables carry the 1/sqrt(32))
-                addv[e] += fmaf(f2[e], z2, fmaf(f1[e], z1, f0[e] * z0)) + c0 + pem[e];
-
-              // publish: neighbour bit mask of the row, and penalty + local ordered by node id
-              uint32_t nbw[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                if (p < np) {
-                  const int nd = node[e];
-                  const uint32_t bit = 1u << (nd & 31);
-                  nbw[0] |= (nd >> 5) == 0 ? bit : 0u; nbw[1] |= (nd >> 5) == 1 ? bit : 0u;
-                  nbw[2] |= (nd >> 5) == 2 ? bit : 0u; nbw[3] |= (nd >> 5) == 3 ? bit : 0u;
-                }
-              }
-#pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                nbw[w] |= __shfl_xor_sync(FULL, nbw[w], 1);
-                nbw[w] |= __shfl_xor_sync(FULL, nbw[w], 2);
-                nbw[w] |= __shfl_xor_sync(FULL, nbw[w], 4);
-              }
-              const int pc1 = __popc(nbw[0]), pc2 = pc1 + __popc(nbw[1]), pc3 = pc2 + __popc(nbw[2]);
-#pragma unroll
-              for (int e = 0; e < MAXE; ++e) {
-                const int p = s8 + 8 * e;
-                if (p < np) {
-                  const int nd = node[e], wd = nd >> 5;
-                  const uint32_t below = pick4(nbw, wd) & ((1u << (nd & 31)) - 1u);
-                  const int rank = (wd == 0 ? 0 : (wd == 1 ? pc1 : (wd == 2 ? pc2 : pc3))) + __popc(below);
-                  sAdd[myr * K1 + rank] = addv[e];
-                }
-              }
-              if (row_ok && s8 < 4) sNb[myr * 4 + s8] = pick4(nbw, s8);
-            }
-            PHASE_MARK(2);
-          }
         }
 
         // ---- O = P V accumulated: normalise, fp16 hi/lo -> O operand (TMEM, over the dead Q operand) ------------
-        mbar_wait(bar_grp, grp_phase);
-        grp_phase ^= 1;
+        mbar_wait(bar_grp, step_par);
         umma::fence_after_sync();
         {
           uint32_t orr[32], hw[16], lw[16];            // heads 4*grp + 2*kh, + 1: 32 consecutive accumulator columns
@@ -650,13 +791,13 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             umma::mma_f16_ts(d, tm + TC_COL_Q + 8 * ks, umma::make_desc(opE + ks * 2 * lboN, lboN, 128), idescS, true);
           umma::commit(bar_sc);
         }
-        PHASE_MARK(3);
+        PHASE_MARK(7);
 
         // ---- B3: logits of this thread's node columns [wsub*CQ, wsub*CQ + CQ) -----------------------------------
-        mbar_wait(bar_sc, sc_phase);
-        sc_phase ^= 1;
+        mbar_wait(bar_sc, step_par);
+        step_par ^= 1u;
         umma::fence_after_sync();
-        PHASE_MARK(7);
+        PHASE_MARK(8);
         {
           uint32_t xr[28];
           const int c0n = wsub * CQ;
@@ -680,7 +821,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             rbase += wd > 0 ? __popc(nbw[0]) : 0;
             rbase += wd > 1 ? __popc(nbw[1]) : 0;
             rbase += wd > 2 ? __popc(nbw[2]) : 0;
-            const float* arow = sAdd + rc * K1 + rbase;
+            const float* arow = sAdd + rc * KT + rbase;
             float* lo = A.out_logits ? A.out_logits + ((size_t)b * A.M + row0 + row) * N1 : nullptr;
             // pass 1: pre-activation x = score + eb + {penalty + local | xi}; -inf where masked; first maximum
             float xmax = -INFINITY;
@@ -736,7 +877,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           sXm[wsub * 128 + row] = best;
           reinterpret_cast<int*>(sXl)[wsub * 128 + row] = bidx;
         }
-        PHASE_MARK(4);
+        PHASE_MARK(9);
       }
       __syncthreads();
 
@@ -798,13 +939,13 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             uint32_t mk = mine | big;
             if (wsub == 0 && fin) mk &= ~1u;               // finished rows may stay at the depot
             sVis[rc * 4 + wsub] = mine;
-            sMask[rc * 4 + wsub] = mk;
+            sMask[wsub * 128 + rc] = mk;
           }
         } else {
           if (wsub < W) {
             const uint32_t mine = pick4(vw, wsub);
             sVis[rc * 4 + wsub] = mine;
-            sMask[rc * 4 + wsub] = mine;
+            sMask[wsub * 128 + rc] = mine;
           }
         }
         live_after = !fin;
@@ -826,10 +967,10 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
           if (t < A.t_max) A.tours[((size_t)b * A.M + row0 + row) * A.t_max + t] = (int16_t)sl;
         }
       }
-      PHASE_MARK(5);
+      PHASE_MARK(10);
       if (A.single_step) break;
       bool more = __syncthreads_or(live_after ? 1 : 0) != 0;
-      PHASE_MARK(6);
+      PHASE_MARK(11);
       if (!CVRP) more = (t + 1) < N1;
       if (!more || t + 1 >= A.t_max) { ++t; break; }
     }
@@ -849,7 +990,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         }
         const size_t g = (size_t)b * A.M + row0 + r;
         A.reward[g] = -len;
-        if (A.logp) A.logp[g] = sLogp[r];
+        if (A.logp) A.logp[g] = 0.f;                 // greedy decoding: no log-likelihood
       }
       if (tid == 0) A.n_steps[b * A.ns_stride + tile] = t;
     }
@@ -860,23 +1001,23 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
   if (warp == 0) umma::tmem_dealloc(tm, 512);
 #ifdef ELG_PHASE_TIMING
   if (tid == 0)
-    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_clk[i], pclk[i]);
+    for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_clk[i], pclk[i]);
 #endif
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// local sequence length / 8: 4 (<= 32 positions) or 6 (<= 48); longer local sequences do not fit the tensor-memory plan
 static int tc_maxe(const elg_model_desc* d) {
   const int KT = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
-  return KT <= 32 ? 4 : (KT <= 48 ? 6 : 8);
+  return KT <= 32 ? 4 : (KT <= 48 ? 6 : 0);
 }
 
 // Largest row tile (multiple of 4, <= 112) whose layout fits the 227 KB of one SM; 0 = none
 int rollout_tc_max_rows(const elg_model_desc* d, int N1) {
-  if (N1 > N_RES_MAX) return 0;
+  if (N1 > N_RES_MAX || tc_maxe(d) == 0) return 0;
   const int K1 = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
-  for (int mt = TC_MT_MAX; mt >= 4; mt -= 4)
-    if ((size_t)make_tc_layout(N1, mt, tc_maxe(d) * 8, K1).total * sizeof(float) <= 227 * 1024) return mt;
-  return 0;
+  (void)K1;
+  return TC_MT_MAX;
 }
 
 // Tiles per aug-instance the tensor-core kernel would use for (B, M, N1); 0 = the shape is not eligible
@@ -900,7 +1041,8 @@ int launch_rollout_tc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) 
   a.MT = mt;
   const int maxe = tc_maxe(d);
   const int K1 = d->local_k + (d->problem == ELG_CVRP ? 1 : 0);
-  const size_t smem = (size_t)make_tc_layout(a.N1, mt, maxe * 8, K1).total * sizeof(float);
+  const size_t smem = (size_t)(maxe == 4 ? TcL<32>::total : TcL<48>::total) * sizeof(float);
+  (void)K1;
   int dev = 0, sms = 148;
   ELG_CUDA_OK(cudaGetDevice(&dev));
   ELG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -912,9 +1054,9 @@ int launch_rollout_tc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) 
     rollout_tc_kernel<P, ME><<<grid, RT, smem, st>>>(a);                                                           \
   } while (0)
   if (d->problem == ELG_CVRP) {
-    if (maxe == 4) ELG_TK(ELG_CVRP, 4); else if (maxe == 6) ELG_TK(ELG_CVRP, 6); else ELG_TK(ELG_CVRP, 8);
+    if (maxe == 4) ELG_TK(ELG_CVRP, 4); else ELG_TK(ELG_CVRP, 6);
   } else {
-    if (maxe == 4) ELG_TK(ELG_TSP, 4); else if (maxe == 6) ELG_TK(ELG_TSP, 6); else ELG_TK(ELG_TSP, 8);
+    if (maxe == 4) ELG_TK(ELG_TSP, 4); else ELG_TK(ELG_TSP, 6);
   }
 #undef ELG_TK
   ELG_LAUNCH_OK();
@@ -924,9 +1066,9 @@ int launch_rollout_tc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) 
 }  // namespace elg
 
 #ifdef ELG_PHASE_TIMING
-extern "C" int elg_debug_phase_clocks_tc(unsigned long long* out8, int reset) {
-  ELG_CUDA_OK(cudaMemcpyFromSymbol(out8, elg::g_phase_clk, sizeof(unsigned long long) * 8));
-  if (reset) { unsigned long long z[8] = {0}; ELG_CUDA_OK(cudaMemcpyToSymbol(elg::g_phase_clk, z, sizeof(z))); }
+extern "C" int elg_debug_phase_clocks_tc(unsigned long long* out16, int reset) {
+  ELG_CUDA_OK(cudaMemcpyFromSymbol(out16, elg::g_phase_clk, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; ELG_CUDA_OK(cudaMemcpyToSymbol(elg::g_phase_clk, z, sizeof(z))); }
   return ELG_OK;
 }
 #endif

@@ -71,6 +71,9 @@ __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void st4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
+__device__ __forceinline__ void st2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
 // strided register lists (r[0], r[S], r[2S], ...): lets hi / lo words interleaved in one array go out as wide stores
 template <int S>
 __device__ __forceinline__ void st4s(uint32_t taddr, const uint32_t* r) {

@@ -111,12 +111,14 @@ typedef struct elg_tables {
   float* qfirst;          /* [B][N1][E]   tsp: per-node first-node query; NULL for cvrp          */
   void* nbr;              /* neighbour lists sorted by (distance, index); elg_nbr_bytes() per batch:
                              resident variant (elg_rollout_resident() == 1): per node ELG_NBR_NODE_BYTES(N1) bytes =
-                               uint8 [ELG_NBR_STRIDE] list, 8-way interleaved, then float2 [N1] (distance, angle) to every node
+                               uint8 [ELG_NBR_STRIDE] list, 8-way interleaved, then float2 [N1] (distance, angle) to every node,
+                               then float4 [N1] per list entry in rank order: (distance, angle, demand, node id bits)
                              larger:                       uint16 [B][N1][ELG_NBR16_STRIDE(NL)], rank order  */
 } elg_tables;
 
 #define ELG_NBR_STRIDE 128                          /* list bytes per node, resident variant          */
-#define ELG_NBR_NODE_BYTES(N1) (ELG_NBR_STRIDE + 8 * (((N1) + 1) & ~1))   /* list + pair features, resident variant */
+#define ELG_NBR_PAIR_BYTES(N1) (8 * (((N1) + 1) & ~1))                     /* pair features indexed by node id       */
+#define ELG_NBR_NODE_BYTES(N1) (ELG_NBR_STRIDE + ELG_NBR_PAIR_BYTES(N1) + 16 * (N1))   /* list + pair features + rank-ordered records */
 #define ELG_NBR16_STRIDE(NL) (((NL) + 63) & ~63)    /* uint16 entries per node, streaming variant     */
 #define ELG_MAX_NODES_RESIDENT 112                  /* upper bound of the resident variant (also needs to fit smem) */
 #define ELG_MAX_NODES 8192                          /* largest instance the rollout supports          */

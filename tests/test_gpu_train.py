@@ -314,9 +314,11 @@ def test_encode_train_equals_encode_bit_for_bit(kind):
     for name in ("enc", "k", "v", "qtab", "eb", "e"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     N1 = int(xy.shape[1])
-    per = 128 + 8 * ((N1 + 1) & ~1)                     # ELG_NBR_NODE_BYTES: list + (distance, angle) pairs; the pad entry is never written
-    na, nb = a.nbr.view(-1, per)[:, :128 + 8 * N1], b.nbr.view(-1, per)[:, :128 + 8 * N1]
-    assert torch.equal(na, nb)
+    pair = 8 * ((N1 + 1) & ~1)
+    per = 128 + pair + 16 * N1                          # ELG_NBR_NODE_BYTES: list + (distance, angle) pairs + rank-ordered records
+    va, vb = a.nbr.view(-1, per), b.nbr.view(-1, per)
+    assert torch.equal(va[:, :128 + 8 * N1], vb[:, :128 + 8 * N1])      # the pad entry of the pair table is never written
+    assert torch.equal(va[:, 128 + pair:], vb[:, 128 + pair:])
     rows = xy.shape[0] * xy.shape[1]
     sv = saved.view(torch.float32)
     last_t2_off = (5 * (8 * 128 + 512) + 7 * 128 + 512) * rows          # layer 5, pre-norm sum of the second sub-layer
