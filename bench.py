@@ -33,11 +33,26 @@ N_NODES, POMO, AUG = 100, 100, 8
 WEIGHT_SEED, INSTANCE_SEED = 1234, 1234
 ALG_BYTES_PER_AUG_STEP = 161548        # K+V+enc re-read + node statics + row state, CVRP100
 ALG_FLOP_PER_ROW_STEP = 329088         # reference arithmetic per decode row-step, CVRP100
-# dram__bytes_read.sum + dram__bytes_write.sum of the rollout kernel from the ncu --set full capture
-# (profiles/r01_rollout_tc_ncu.md: 875.8 MB for a 2400-aug-instance launch): the tensor-core operands are read once per
-# rollout, the per-step gathers (query rows, pair features) mostly hit L2
-NCU_DRAM_BYTES_PER_AUG_INSTANCE = 875.8e6 / 2400
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+SMS, LANES = 148, 128
+FP32_PEAK_TFLOPS = SMS * LANES * 2 * 1.965e9 / 1e12
+# Per-pipe work of ONE decode row-step in the folded formulation the kernel computes (DESIGN.md 5.1 "Roofline", CVRP100:
+# N+1 = 101 nodes, local sequence 41).  Tensor pipe: Q K^T, P V, O E'^T (3 x 12,928 MAC), the local policy's W (Wv PE)
+# (1,312) and ol [PW | ZW] (1,440) = 41,536 MAC, each issued three times (split precision: lo*hi, hi*lo, hi*hi).
+# FMA/ALU pipe (thread operations): query row, the two softmaxes around their exponentials, local scores / sums, final
+# logits, fp32 -> fp16 hi/lo conversions, environment step and list walk on bit masks.  XU pipe: one exp2 per (head, key).
+PIPE_TENSOR_FLOP = 41536 * 2 * 3
+PIPE_FMA_OPS = 2 * (128 + 492 + 492 + 96 + 164) + 3232 + 656 + 303 + 3780 + 1200
+PIPE_XU_OPS = 8 * 101 + 4 * 41
+
+
+def ncu_traffic():
+    """dram__bytes of the rollout kernel per aug-instance from the committed ncu --set full capture of THIS kernel
+    (profiles/ncu_traffic.json: {sha, kernel, dram_bytes_per_aug_instance, source}); None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -97,8 +112,10 @@ def make_instances(n, seed):
 
 
 # ------------------------------------------------------------------------------------------- CPU arms
-def cpu_rollout_rate(n_inst, seed, threads=None):
-    """Reference algorithm on the host (oracle port, torch CPU): instances/s for one batch of n_inst."""
+def cpu_rollout_rate(n_inst, seed, threads=None, device=None, keep=None):
+    """Reference algorithm (oracle port, torch eager): instances/s for one batch of n_inst on the host cores, or, with
+    device='cuda:0', the same torch code on the GPU (SURVEY 8d "reference torch-CUDA eager", informative).  `keep` (dict)
+    receives the tours / rewards / per-instance costs for the in-bench parity check."""
     import torch
     from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
     from oracle import elg_oracle as O
@@ -106,14 +123,46 @@ def cpu_rollout_rate(n_inst, seed, threads=None):
         torch.set_num_threads(threads)
     W = O.Weights(synthetic_state_dict("cvrp", seed=WEIGHT_SEED), "cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]))
     data = make_instances(n_inst, seed)
+    ctx = torch.device(device) if device else torch.device("cpu")
+    if device:
+        W.sd = {k: v.to(device) for k, v in W.sd.items()}
+        data = {k: v.to(device) for k, v in data.items()}
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
-    with torch.no_grad():
+    with torch.no_grad(), ctx:
         prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], AUG)
         perm = O.start_permutation("cvrp", N_NODES, POMO, seed=seed)
+        if device:
+            perm = perm.to(device)
         tours, _, reward = O.rollout(W, prob, POMO, perm, "greedy")
-        O.best_of(reward, AUG, n_inst)
+        _, aug_cost = O.best_of(reward, AUG, n_inst)
+        if device:
+            torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.update(tours=tours.cpu(), reward=reward.cpu(), aug_cost=aug_cost.cpu(), perm=perm.cpu())
     return n_inst / dt, dt, int(tours.shape[2])
+
+
+def gpu_vs_oracle(model, env, dev, n_inst, seed, ref):
+    """In-bench parity: the instances the CPU baseline just solved, through our CUDA path with the same start permutation."""
+    import torch
+    from elg_b200.cvrp.test import solve_batch
+    data = {k: v.to(dev) for k, v in make_instances(n_inst, seed).items()}
+    random.seed(seed)
+    _, aug, sol, rew = solve_batch(model, env, data, AUG)
+    sol, rew, aug = sol.cpu(), rew.cpu(), aug.cpu()
+    rt = ref["tours"]
+    T = max(sol.shape[2], rt.shape[2])
+    a = torch.zeros(sol.shape[0], sol.shape[1], T, dtype=torch.long); a[:, :, :sol.shape[2]] = sol
+    b = torch.zeros_like(a); b[:, :, :rt.shape[2]] = rt
+    same = (a == b).all(dim=2)
+    rel = ((rew - ref["reward"]).abs() / ref["reward"].abs())[same]
+    return {"instances": n_inst, "rows": int(same.numel()), "rows_identical_frac": float(same.float().mean()),
+            "reward_max_rel_err_on_identical_rows": float(rel.max()) if rel.numel() else None,
+            "best_cost_max_rel_err": float(((aug - ref["aug_cost"]).abs() / ref["aug_cost"]).max()),
+            "best_cost_identical": int(((aug - ref["aug_cost"]).abs() / ref["aug_cost"] < 1e-6).sum()),
+            "checker": "oracle port (torch CPU) on the cpu_baseline sample, same weights / instances / start permutation"}
 
 
 def run_reference(args):
@@ -247,10 +296,27 @@ def run_ours(args):
     ach_gbs = ALG_BYTES_PER_AUG_STEP * aug_steps / (k_ms * 1e-3) / 1e9
     ach_tf = ALG_FLOP_PER_ROW_STEP * row_steps / (k_ms * 1e-3) / 1e12
 
+    # config 3 (REINFORCE training step, NCCL all-reduce of the gradient for N > 1) rides along so that every driver run
+    # puts it on record; `--workload train` prints the same measurement as its own line
+    train = None
+    if not args.no_train:
+        train = measure_train(args, world, rank, local, dev, short=True)
+
     if rank == 0:
         n_total = nb * world * args.steps
         value = n_total / (ms_dev * 1e-3)
         e2e = n_total / (ms_e2e * 1e-3)
+        n_launch = max(len(events), 1)
+        # per-pipe lower bounds of the rollout kernel for the row-steps it actually processed (all N GPUs of this rank's view
+        # are identical, so rank 0's kernel stands for the job)
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        tc_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        t_tensor = PIPE_TENSOR_FLOP * row_steps / (tc_peak * 1e12) * 1e3                                  # ms
+        t_fma = PIPE_FMA_OPS * row_steps / (SMS * LANES * sm_clock * 1e6) * 1e3
+        t_xu = PIPE_XU_OPS * row_steps / (SMS * 16 * sm_clock * 1e6) * 1e3
+        t_bound = max(t_tensor, t_fma, t_xu)
+        bound_pipe = "fma" if t_bound == t_fma else ("tensor" if t_bound == t_tensor else "xu")
+        traffic = ncu_traffic()
         line = {
             "metric": "CVRP100 instances/s (POMO x8 aug, greedy)", "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -261,31 +327,60 @@ def run_ours(args):
                     "d2h_bytes_per_step": 2 * nb * 4 + AUG * nb * POMO * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
+            # The rollout kernel keeps K'/V/E' resident in shared memory, so it is compute-side bound; `frac` is the
+            # per-pipe lower bound of its folded arithmetic over the measured time.  The tensor-pipe view
+            # (achieved / peak in TFLOP/s) and the SURVEY 8(d) contract figures are kept beside it.
             "roofline": {"kernel": "rollout_tc_kernel<CVRP> (decode step + env step, whole rollout in one launch)",
-                         "bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach_gbs / peaks["hbm_gbs"], "peak_source": peak_src,
-                         "traffic": NCU_DRAM_BYTES_PER_AUG_INSTANCE * nb * AUG,
-                         "traffic_note": "bytes per launch, scaled from the ncu capture in profiles/r01_rollout_tc_ncu.md",
-                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_AUG_STEP * aug_steps / max(len(events), 1),
-                         "algorithmic_bytes_per_aug_instance_step": ALG_BYTES_PER_AUG_STEP,
-                         "aug_instance_steps_per_launch": aug_steps / max(len(events), 1),
-                         "kernel_ms_per_launch": k_ms / max(len(events), 1),
+                         "bound": "tensor", "achieved": PIPE_TENSOR_FLOP * row_steps / (k_ms * 1e-3) / 1e12,
+                         "peak": tc_peak, "unit": "TFLOP/s",
+                         "frac": t_tensor / k_ms, "peak_source": peak_src + (", sustained (kernel of a long step)" if "bf16_tflops_sustained" in peaks else ", burst"),
+                         "traffic": (traffic["dram_bytes_per_aug_instance"] * nb * AUG) if traffic else None,
+                         "traffic_source": ({k: traffic[k] for k in ("sha", "source") if k in traffic} if traffic else None),
+                         "pipe_model": {"tensor_ms": t_tensor / n_launch, "fma_ms": t_fma / n_launch, "xu_ms": t_xu / n_launch,
+                                        "bound_ms": t_bound / n_launch, "serial_ms": (t_tensor + t_fma + t_xu) / n_launch,
+                                        "measured_ms": k_ms / n_launch, "binding_pipe": bound_pipe,
+                                        "frac_of_bound": t_bound / k_ms, "frac_of_serial": (t_tensor + t_fma + t_xu) / k_ms,
+                                        "per_row_step": {"tensor_flop_issued": PIPE_TENSOR_FLOP, "fma_alu_thread_ops": PIPE_FMA_OPS,
+                                                         "xu_ops": PIPE_XU_OPS},
+                                        "us_per_sm_step": k_ms * 1e3 * SMS / max(aug_steps, 1),
+                                        "note": "lower bounds per pipe for the folded arithmetic (split-precision MMAs as issued, "
+                                                "100 live rows); max() = perfect overlap of the pipes, serial = none"},
+                         "row_steps_per_launch": row_steps / n_launch,
+                         "aug_instance_steps_per_launch": aug_steps / n_launch,
+                         "kernel_ms_per_launch": k_ms / n_launch,
                          "kernel_share_of_step": k_ms / ms_dev,
-                         "note": "K'/V/E' stay resident in shared memory for the whole rollout, so the streaming-model "
-                                 "HBM bytes are (by design) not moved; the kernel is issue/latency-bound (ncu: ~50% issue "
-                                 "slots, tensor pipe 5%), see fp32 for the throughput-equivalent"},
-            "fp32": {"achieved": ach_tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach_tf / FP32_PEAK_TFLOPS,
-                     "flop_per_row_step": ALG_FLOP_PER_ROW_STEP,
-                     "note": "reference-arithmetic FLOPs (SURVEY 8d) / rollout-kernel time; peak = 148 SM x 128 FMA x 2 x 1.965 GHz"},
+                         "contract_hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
+                                          "algorithmic_bytes_per_aug_instance_step": ALG_BYTES_PER_AUG_STEP,
+                                          "note": "SURVEY 8(d) streaming model; the operands stay in shared memory, so these bytes "
+                                                  "are by design not moved (see traffic)"},
+                         "contract_fp32": {"achieved": ach_tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                           "frac": ach_tf / FP32_PEAK_TFLOPS, "flop_per_row_step": ALG_FLOP_PER_ROW_STEP,
+                                           "note": "reference-arithmetic FLOPs (SURVEY 8d) / kernel time: a throughput-equivalent, "
+                                                   "not a utilisation (the folds remove 2.4x of them, the contractions run on tcgen05)"}},
             "mean_aug_cost": mean_cost, "rollout_steps_T": T_list,
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            rate, dt, T = cpu_rollout_rate(args.cpu_sample, INSTANCE_SEED)
+            ref = {}
+            rate, dt, T = cpu_rollout_rate(args.cpu_sample, INSTANCE_SEED, keep=ref)
             line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d CVRP100 instances (x8 aug x 100 POMO rows), one batch, %.1f s, T=%d; "
                                               "oracle port of the reference's torch-CPU path" % (args.cpu_sample, dt, T),
                                     "host_cpu_count": os.cpu_count()}
+            try:
+                line["parity"] = gpu_vs_oracle(model, env, dev, args.cpu_sample, INSTANCE_SEED, ref)
+            except Exception as e:      # the bench line must survive a checker problem
+                line["parity"] = {"error": repr(e)[:200]}
+            try:
+                cpu_rollout_rate(2, INSTANCE_SEED, device=dev)                      # warm-up (cuBLAS handles, allocator)
+                rate_g, dt_g, T_g = cpu_rollout_rate(args.cpu_sample, INSTANCE_SEED, device=dev)
+                line["ref_cuda_eager"] = {"value": rate_g, "unit": "instances/s", "kind": "port",
+                                          "sample": "the same %d instances, the oracle port's torch code on %s (eager, fp32, no "
+                                                    "TF32), %.1f s, T=%d" % (args.cpu_sample, dev, dt_g, T_g)}
+            except Exception as e:
+                line["ref_cuda_eager"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -304,13 +399,9 @@ def train_config(batch_per_gpu, n_gpus):
 
 
 def run_train(args):
-    """BASELINE.json configs[2]: one step = generate/load a batch, encoder (activations kept), sample rollout, REINFORCE
-    backward, all-reduce of the gradient (N > 1), Adam, re-fold of the decoder tables."""
+    """`--workload train`: BASELINE.json configs[2] as its own bench line."""
     import torch
     import torch.distributed as dist
-    from elg_b200 import _lib, engine
-    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
-    from elg_b200.trainer import Trainer
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -318,10 +409,27 @@ def run_train(args):
     dev = "cuda:%d" % local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    line = measure_train(args, world, rank, local, dev, short=False)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_train(args, world, rank, local, dev, short):
+    """BASELINE.json configs[2]: one step = generate/load a batch, encoder (activations kept), sample rollout, REINFORCE
+    backward, all-reduce of the gradient (N > 1), Adam, re-fold of the decoder tables.  Returns the bench line (rank 0;
+    None elsewhere); short = the condensed form embedded in the inference line."""
+    import torch
+    import torch.distributed as dist
+    from elg_b200 import _lib, engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_state_dict
+    from elg_b200.trainer import Trainer
     tr = Trainer("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]), synthetic_state_dict("cvrp", seed=WEIGHT_SEED), dev,
                  chunk_steps=args.chunk_steps)
     nb = args.train_batch
-    total_steps = args.warmup + args.steps
+    steps = min(args.steps, 10) if short else args.steps
+    total_steps = args.warmup + steps
     host = [{k: v.pin_memory() for k, v in make_instances(nb, INSTANCE_SEED + 7919 * s + rank).items()} for s in range(total_steps)]
     dev_batches = [{k: v.to(dev) for k, v in h.items()} for h in host]
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -382,37 +490,64 @@ def run_train(args):
     ms_e2e, _, clocks_e2e, _, _, _ = timed(step_e2e)
     bwd_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in events)
     row_steps = sum(n for _, _, n in events)
-    if rank == 0:
-        n_total = nb * world * args.steps
-        line = {"metric": TRAIN_METRIC, "value": n_total / (ms_dev * 1e-3), "unit": "instances/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(nb, world),
-                "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "instances/s",
-                        "h2d_bytes_per_step": nb * (2 + 2 * N_NODES + N_NODES) * 4, "d2h_bytes_per_step": 4 + 4,
-                        "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "clocks_e2e": clocks_e2e,
-                "mean_sampled_cost_per_step": costs, "rollout_steps_T": Ts,
-                "grad_allreduce_bytes": int(tr.grads.numel()) * 4 if world > 1 else 0}
-        peaks, peak_src = measured_peaks()
-        # streaming model of the backward: per aug-instance-step the tables K', V, E' are read for the forward recompute
-        # and again for the gradients (2 x SURVEY 8d's 161,548 B), and the per-row-step vectors are written and re-read
-        alg = 2 * ALG_BYTES_PER_AUG_STEP * (row_steps / POMO) + row_steps * 2 * (104 + 104 + 128) * 4
-        ach = alg / (bwd_ms * 1e-3) / 1e9
-        line["roofline"] = {"kernel": "elg_reinforce_backward (replay, local/global decode backward, table + encoder backward)",
-                            "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                            "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_step": alg / max(len(events), 1),
-                            "ms_per_step": bwd_ms / max(len(events), 1), "share_of_step": bwd_ms / ms_dev,
-                            "row_steps_per_step": row_steps / max(len(events), 1),
-                            "note": "the instance tables are staged in shared memory once per 4 steps, so HBM is not what binds: "
-                                    "global_bwd_kernel runs at 60 % of the shared-memory wavefront peak (profiles/r01_train_ncu.md)"}
-        if world == 1 and not args.no_cpu_baseline:
-            rate, dt, T, cores = cpu_train_rate(args.cpu_train_sample, INSTANCE_SEED)
-            line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
-                                    "sample": "%d CVRP100 instances x 100 rollouts, one step, %.1f s, T=%d; oracle port: teacher-forced "
-                                              "forward with autograd graph + backward + Adam on pre-sampled tours" % (args.cpu_train_sample, dt, T)}
-        print(json.dumps(line), flush=True)
+    # the gradient all-reduce on its own (N > 1): one NCCL sum of the packed parameter vector, timed with CUDA events
+    ar_ms = 0.0
     if world > 1:
-        dist.destroy_process_group()
+        from elg_b200.dist import allreduce_mean_gradient
+        g = torch.zeros_like(tr.grads)
+        for _ in range(3):
+            allreduce_mean_gradient(g)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            allreduce_mean_gradient(g)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+    if rank != 0:
+        return None
+    n_total = nb * world * steps
+    grad_bytes = int(tr.grads.numel()) * 4
+    if short:
+        return {"metric": TRAIN_METRIC, "value": n_total / (ms_dev * 1e-3), "unit": "instances/s", "n_gpus": world, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / steps, "scaling": "weak",
+                "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "instances/s", "ms_per_step": ms_e2e / steps,
+                        "h2d_bytes_per_step": nb * (2 + 2 * N_NODES + N_NODES) * 4, "d2h_bytes_per_step": 8},
+                "instances_per_step_per_gpu": nb, "backward_ms_per_step": bwd_ms / max(len(events), 1),
+                "allreduce_ms": ar_ms, "grad_allreduce_bytes": grad_bytes if world > 1 else 0, "collective": "NCCL all-reduce (sum) of the "
+                "packed gradient, 1/world folded into the Adam kernel" if world > 1 else "none (1 GPU)",
+                "gpu_launches": launches, "mean_sampled_cost_first_last": [costs[0], costs[-1]], "rollout_steps_T": Ts,
+                "config": train_config(nb, world)["workload"]}
+    line = {"metric": TRAIN_METRIC, "value": n_total / (ms_dev * 1e-3), "unit": "instances/s", "n_gpus": world,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(nb, world),
+            "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "instances/s",
+                    "h2d_bytes_per_step": nb * (2 + 2 * N_NODES + N_NODES) * 4, "d2h_bytes_per_step": 4 + 4,
+                    "ms_per_step": ms_e2e / steps},
+            "gpu_launches": launches, "clocks": clocks, "clocks_e2e": clocks_e2e,
+            "mean_sampled_cost_per_step": costs, "rollout_steps_T": Ts,
+            "allreduce_ms": ar_ms, "grad_allreduce_bytes": grad_bytes if world > 1 else 0}
+    peaks, peak_src = measured_peaks()
+    # streaming model of the backward: per aug-instance-step the tables K', V, E' are read for the forward recompute
+    # and again for the gradients (2 x SURVEY 8d's 161,548 B), and the per-row-step vectors are written and re-read
+    alg = 2 * ALG_BYTES_PER_AUG_STEP * (row_steps / POMO) + row_steps * 2 * (104 + 104 + 128) * 4
+    ach = alg / (bwd_ms * 1e-3) / 1e9
+    line["roofline"] = {"kernel": "elg_reinforce_backward (replay, local/global decode backward, table + encoder backward)",
+                        "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                        "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_step": alg / max(len(events), 1),
+                        "ms_per_step": bwd_ms / max(len(events), 1), "share_of_step": bwd_ms / ms_dev,
+                        "row_steps_per_step": row_steps / max(len(events), 1),
+                        "note": "the instance tables are staged in shared memory once per 4 steps, so HBM is not what binds: "
+                                "global_bwd_kernel runs at 60 % of the shared-memory wavefront peak (profiles/r01_train_ncu.md)"}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, T, cores = cpu_train_rate(args.cpu_train_sample, INSTANCE_SEED)
+        line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
+                                "sample": "%d CVRP100 instances x 100 rollouts, one step, %.1f s, T=%d; oracle port: teacher-forced "
+                                          "forward with autograd graph + backward + Adam on pre-sampled tours" % (args.cpu_train_sample, dt, T)}
+    return line
 
 
 def cpu_train_rate(n_inst, seed):
@@ -467,6 +602,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="instances per step for --impl reference (bounded sample)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="instances in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the embedded training measurement (config 3) of the inference line")
     ap.add_argument("--workload", default="inference", choices=["inference", "train"],
                     help="inference = BASELINE.json configs[1] (the headline metric); train = configs[2]")
     ap.add_argument("--train-batch", type=int, default=64, help="training instances per step per GPU")

@@ -33,9 +33,8 @@ def rollout(model, env, eval_type='greedy'):
 
 
 def _fused_rollout(model, env, eval_type):
-    """Whole rollout in one launch.  In 'sample' mode the per-step probabilities are not
-    materialised; `probs` is returned as a (B, 1, M) tensor holding exp(sum of log-probs) so that
-    `probs.log().sum(dim=1)` (CVRP/train.py:115) still yields the trajectory log-likelihood."""
+    """Whole rollout in one launch.  In 'sample' mode the per-step probabilities are not materialised;
+    `probs` has the reference's (B, T, M) shape and the trajectory log-likelihood as its log-sum (see _probs_from_logp)."""
     env.reset()
     batch = model._batch
     if batch is None or batch.xy.data_ptr() != env.depot_node_xy.data_ptr():
@@ -48,8 +47,17 @@ def _fused_rollout(model, env, eval_type):
     T = int(n_steps.max().item())
     solutions = tours16[:, :, :T].long()
     env._finish_fused(solutions, reward)
-    probs = None if eval_type == 'greedy' else torch.exp(logp)[:, None, :]
+    probs = None if eval_type == 'greedy' else _probs_from_logp(logp, T)
+    model._last_logp = logp
     return solutions, probs, reward
+
+
+def _probs_from_logp(logp, T):
+    """(B, M) trajectory log-likelihood -> (B, T, M) tensor with the reference's shape whose `probs.log().sum(dim=1)`
+    (CVRP/train.py:115) is that log-likelihood.  The fused rollout does not materialise per-step probabilities; exp(logp) itself
+    underflows fp32 (an untrained CVRP100 policy has log-likelihoods around -360), so every step carries the geometric
+    mean exp(logp / T) -- an expanded view, no memory.  The exact value is also kept as `model._last_logp`."""
+    return torch.exp(logp / T)[:, None, :].expand(-1, T, -1)
 
 
 def augment_xy_data_by_8_fold(problems):

@@ -95,14 +95,16 @@ def validate(problem, trainer, model_params, multiple_width, device, mixed, dist
         sets = [('data/%s_uniform100_1000_seed1234.pkl' % pre, 100, val_samples[0], 'uniform'),
                 ('data/%s_cluster100_1000_seed1234.pkl' % pre, 100, val_samples[1], 'cluster'),
                 ('data/%s_mixed100_1000_seed1234.pkl' % pre, 100, val_samples[2], 'mixed')]
-    else:
-        sets = [('data/%s100_val.pkl' % pre, 100, val_samples[0], 'uniform'), ('data/%s200_val.pkl' % pre, 200, val_samples[1], 'uniform'),
-                ('data/%s500_val.pkl' % pre, 500, val_samples[2], 'uniform')]
+    else:      # file names as the reference spells them: CVRP/train.py:65-69 (vrp100_val), TSP/train.py:62-66 (tsp_100_val)
+        sep = '' if problem == "cvrp" else '_'
+        sets = [('data/%s%s%d_val.pkl' % (pre, sep, size), size, n, 'uniform') for size, n in zip((100, 200, 500), val_samples)]
+    env = Env(multiple_width, device)      # one environment of width multiple_width for every set (CVRP/train.py:43, TSP/train.py:42)
     for path, size, n, dt in sets:
-        width = multiple_width if size == 100 else size
-        env = Env(min(width, size), device)
+        if not os.path.exists(path):
+            print("validation set %s not found: using a seeded generated set of the same size / distribution" % path, flush=True)
         d = dict(distribution, data_type=dt)
-        out.append(test_rollout(problem, _batches(problem, path, size, n, 1000 if size == 100 else 10, d, device, 1234), env, model))
+        batch = 10 if size == 500 else (1000 if (problem == "cvrp" or mixed) else 500)      # the reference's DataLoader batch sizes
+        out.append(test_rollout(problem, _batches(problem, path, size, n, batch, d, device, 1234), env, model))
     return out
 
 
@@ -151,17 +153,25 @@ def train(problem, config, device, dir_path=None, log_path=None, max_steps=None,
         history.append((float(out["loss"]), float(-out["reward"].max(1)[0].mean())))
         if verbose and rank == 0 and (i % 50 == 0):
             print("step %d  J %.5f  training length %.4f" % (i, history[-1][0], history[-1][1]), flush=True)
-        if (i + 1) % p['log_step'] == 0 and rank == 0:
-            val_info = validate(problem, tr, model_params, p['multiple_width'], device, p['mixed'], distribution, val_samples)
-            if file_logger is not None:
-                file_logger.log(val_info)
-            if dir_path:
-                os.makedirs(dir_path, exist_ok=True)
-                ck = tr.checkpoint()
-                ck['step'] = i
-                torch.save(ck, dir_path + '/model_epoch_{}.pt'.format(int((i + 1) / p['log_step'])))
+        if (i + 1) % p['log_step'] == 0:
+            # rank 0 validates and checkpoints; the others wait at the broadcast (not inside the next step's gradient
+            # all-reduce), and every rank gets the validation costs: the curriculum weights `gaps` stay identical
+            val = torch.zeros(3, dtype=torch.float64, device=device)
+            if rank == 0:
+                val_info = validate(problem, tr, model_params, p['multiple_width'], device, p['mixed'], distribution, val_samples)
+                val = torch.tensor(val_info, dtype=torch.float64, device=device)
+                if file_logger is not None:
+                    file_logger.log(val_info)
+                if dir_path:
+                    os.makedirs(dir_path, exist_ok=True)
+                    ck = tr.checkpoint()
+                    ck['step'] = i
+                    torch.save(ck, dir_path + '/model_epoch_{}.pt'.format(int((i + 1) / p['log_step'])))
+            if tr.world > 1:
+                torch.distributed.broadcast(val, src=torch.distributed.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                            group=process_group)
             if p['mixed']:
-                gaps = (np.array(val_info) - opts) / opts
+                gaps = (val.cpu().numpy() - opts) / opts
     return tr, history
 
 
@@ -178,8 +188,11 @@ def main(problem):
     torch.cuda.set_device(local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
+    # seed_everything (CVRP/utils.py:121-128), offset per rank so that the ranks generate different training instances and
+    # sampling streams; the PARAMETERS are rank 0's on every rank (Trainer.sync_weights broadcasts them at construction
+    # and again when the local policy is added)
     seed = config['seed'] + int(os.environ.get("RANK", "0"))
-    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)        # seed_everything, CVRP/utils.py:121-128
+    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
     ts = datetime.datetime.utcnow() + datetime.timedelta(hours=+8)
     ts_name = f'-ts{ts.month}-{ts.day}-{ts.hour}-{ts.minute}-{ts.second}'
     state_dict = None

@@ -37,6 +37,17 @@ class Trainer:
         # without a local policy (decoder.local False, CVRP/models.py:294-297) its keys are not part of the model
         self._slots = slots if self.handle.has_local else {k: o for k, o in slots.items() if k not in self._local_keys}
         self._shapes = {k: tuple(v.shape) for k, v in state_dict.items() if k in self._slots}
+        self.global_step = 0          # never reset: seeds the sampling streams (the optimizer's step_count restarts with it)
+        self.sync_weights()
+
+    def sync_weights(self):
+        """Data-parallel replicas must start from the same parameters: rank 0's packed weights are broadcast (every rank may
+        have built its model from its own RNG, CVRP/train.py:199 under a per-rank seed) and the decoder tables re-folded.
+        Collective: every rank of the group calls it (constructor, add_local_policy, load_checkpoint)."""
+        if self.world > 1:
+            src = torch.distributed.get_global_rank(self.pg, 0) if self.pg is not None else 0
+            torch.distributed.broadcast(self.handle.weights, src=src, group=self.pg)
+            engine.prepare_model(self.handle)
 
     @property
     def has_local(self):
@@ -64,6 +75,7 @@ class Trainer:
         self.handle.desc.flags |= _lib.FLAG_ENSEMBLE
         self.handle.has_local = True
         engine.prepare_model(self.handle)
+        self.sync_weights()           # the fresh local parameters were drawn per rank: rank 0's copy wins
         self.exp_avg.zero_(); self.exp_avg_sq.zero_()
         self.step_count = 0
 
@@ -93,10 +105,11 @@ class Trainer:
         engine.prepare_model(self.handle)
 
     def step(self, data, M, start_nodes=None, seed=None):
-        if seed is None:
-            seed = (torch.initial_seed() * 1000003 + self.step_count) & (2 ** 63 - 1)
+        if seed is None:       # a counter that survives the optimizer restart of add_local_policy: no sampling stream is replayed
+            seed = (torch.initial_seed() * 1000003 + self.global_step) & (2 ** 63 - 1)
         out = self.forward_backward(data, M, start_nodes, seed)
         self.optimizer_step()
+        self.global_step += 1
         return out
 
     # ---- reference-format state (CVRP/train.py:137-141)
@@ -134,8 +147,20 @@ class Trainer:
             self._pack({k: st[i]["exp_avg"] for i, k in enumerate(keys)}, self.exp_avg)
             self._pack({k: st[i]["exp_avg_sq"] for i, k in enumerate(keys)}, self.exp_avg_sq)
             self.step_count = int(st[0]["step"])
+        else:
+            self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+            self.step_count = 0
+        self.global_step = int(ck.get("global_step", self.step_count))
 
     def checkpoint(self):
-        return {"step": self.step_count, "model_state_dict": self.state_dict(),
-                "optimizer_state_dict": {"exp_avg": self.unpack(self.exp_avg), "exp_avg_sq": self.unpack(self.exp_avg_sq),
-                                         "step": self.step_count, "lr": self.lr, "weight_decay": self.weight_decay}}
+        """The reference's checkpoint dict (CVRP/train.py:137-141).  `optimizer_state_dict` has the layout of
+        torch.optim.Adam.state_dict() -- per-parameter state in model.parameters() order (= state_dict order) plus
+        param_groups -- so that the reference's `optimizer.load_state_dict` accepts it."""
+        m, v = self.unpack(self.exp_avg), self.unpack(self.exp_avg_sq)
+        keys = list(self._slots)
+        state = {i: {"step": torch.tensor(float(self.step_count)), "exp_avg": m[k], "exp_avg_sq": v[k]} for i, k in enumerate(keys)}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(keys)))}
+        return {"step": self.step_count, "global_step": self.global_step, "model_state_dict": self.state_dict(),
+                "optimizer_state_dict": {"state": state if self.step_count > 0 else {}, "param_groups": [group]}}

@@ -37,7 +37,8 @@ def _fused_rollout(model, env, eval_type):
     tours16, reward, logp, n_steps = engine.rollout(batch, M, start, mode=eval_type, seed=model._next_seed())
     solutions = tours16[:, :, :env.problem_size].long()
     env._finish_fused(solutions)
-    probs = None if eval_type == 'greedy' else torch.exp(logp)[:, None, :]
+    probs = None if eval_type == 'greedy' else _probs_from_logp(logp, env.problem_size)
+    model._last_logp = logp
     return solutions, probs, reward
 
 

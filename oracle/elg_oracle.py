@@ -26,6 +26,7 @@ Reference map (file:line under /root/reference):
   encode              CVRP/models.py:199-269,506-562, TSP/models.py:134-194,387-423
   decoder_cache       CVRP/models.py:300-308, TSP/models.py:227-242
   decode_logits       CVRP/models.py:322-423 + 51-175, TSP/models.py:244-303 + 48-110
+  cur_feature         CVRP/CVRPEnv.py:291-318, TSP/TSPEnv.py:135-156
   select              CVRP/CVRPModel.py:36-75, TSP/TSPModel.py:26-64
   cvrp_env_step       CVRP/CVRPEnv.py:190-249
   tsp_env_step        TSP/TSPEnv.py:108-133
@@ -208,8 +209,26 @@ def _position_table(n_pos, emb, dtype):
     return torch.cat((torch.sin(ang), torch.cos(ang)), dim=1)
 
 
-def _neighbourhood(W, prob, cur, masked, load):
+def cur_feature(prob, cur, load=None):
+    """The per-step feature tensors the reference's environments hand to the model: CVRPEnv.get_cur_feature
+    (CVRP/CVRPEnv.py:291-318) -> (cur_dist, cur_theta, relative_xy, norm_demand); TSPEnv.get_local_feature
+    (TSP/TSPEnv.py:135-156) -> the first three.  cur_dist is a row of the precomputed distance matrix, theta =
+    atan2(rel_y, rel_x), norm_demand = demand / load for EVERY node (0/0 = nan at the depot and +-inf at customers
+    when the load is exactly 0 or slightly negative -- SURVEY A.6; the model only ever reads valid customers)."""
+    B, N1, _ = prob.xy.shape
+    cur_dist = prob.dist.gather(1, cur[:, :, None].expand(-1, -1, N1))
+    rel = prob.xy[:, None, :, :] - prob.xy.gather(1, cur[:, :, None].expand(-1, -1, 2))[:, :, None, :]
+    theta = torch.atan2(rel[..., 1], rel[..., 0])
+    if prob.kind == "cvrp":
+        return cur_dist, theta, rel, prob.demand[:, None, :] / load[:, :, None]
+    return cur_dist, theta, rel
+
+
+def _neighbourhood(W, prob, cur, masked, load, feats=None):
     """k nearest valid nodes per row, ascending distance; returns dict of (B, M, L) tensors.
+
+    feats = (cur_dist, cur_theta, norm_demand | None): take the per-node features from the caller (what the reference's
+    local_policy_att.forward receives from the environment, CVRP/models.py:51-60) instead of recomputing them.
 
     valid = not masked and (cvrp) not the depot.  Slots past a row's valid count are
     flagged `pad` and carry zero features, as in the reference (inf -> 0 padding).
@@ -217,7 +236,7 @@ def _neighbourhood(W, prob, cur, masked, load):
     """
     B, M, N1 = masked.shape
     k = W.p["local_size"][0]
-    row_dist = prob.dist.gather(1, cur[:, :, None].expand(-1, -1, N1))
+    row_dist = prob.dist.gather(1, cur[:, :, None].expand(-1, -1, N1)) if feats is None else feats[0]
     excl = masked.clone()
     if W.kind == "cvrp":
         excl[:, :, 0] = True
@@ -239,11 +258,16 @@ def _neighbourhood(W, prob, cur, masked, load):
         idx = cur.new_zeros(B, M, 0)
         pad = torch.zeros(B, M, 0, dtype=torch.bool)
         dmax = row_dist.new_zeros(B, M, 1)
-    rel = prob.xy[:, None, :, :] - prob.xy.gather(1, cur[:, :, None].expand(-1, -1, 2))[:, :, None, :]
-    theta = torch.atan2(rel[..., 1], rel[..., 0]).gather(2, idx).masked_fill(pad, 0.0)
+    if feats is None:
+        rel = prob.xy[:, None, :, :] - prob.xy.gather(1, cur[:, :, None].expand(-1, -1, 2))[:, :, None, :]
+        theta_all = torch.atan2(rel[..., 1], rel[..., 0])
+    else:
+        theta_all = feats[1]
+    theta = theta_all.gather(2, idx).masked_fill(pad, 0.0)
     out.update(d=d, idx=idx, pad=pad, dmax=dmax, theta=theta)
     if W.kind == "cvrp":
-        nd = (prob.demand[:, None, :] / load[:, :, None]).gather(2, idx).masked_fill(pad, 0.0)
+        nd_all = prob.demand[:, None, :] / load[:, :, None] if feats is None else feats[2]
+        nd = nd_all.gather(2, idx).masked_fill(pad, 0.0)
         out["norm_demand"] = nd
     return out
 
@@ -278,8 +302,9 @@ def _local_scores(W, nb, masked):
     return torch.einsum("bme,bmle->bml", mh, ik) / math.sqrt(e)
 
 
-def decode_logits(W, prob, cache, cur, masked, load=None):
+def decode_logits(W, prob, cache, cur, masked, load=None, feats=None):
     """Masked logits (the tensor the reference feeds to its final softmax), shape (B, M, N1).
+    feats: optional environment features for the local policy / distance penalty, see _neighbourhood.
 
     cur (B, M) int64; masked (B, M, N1) bool (True = -inf in the reference's ninf_mask);
     load (B, M) for cvrp.
@@ -298,7 +323,7 @@ def decode_logits(W, prob, cache, cur, masked, load=None):
     mh = F.linear(o, W["decoder.multi_head_combine.weight"], W["decoder.multi_head_combine.bias"])
     score = mh @ cache.enc.transpose(1, 2) / math.sqrt(E)
 
-    nb = _neighbourhood(W, prob, cur, masked, load)
+    nb = _neighbourhood(W, prob, cur, masked, load, feats)
     if p["distance_penalty"]:
         pen = torch.full_like(score, float(p["xi"]))
         if W.kind == "cvrp":
