@@ -150,7 +150,7 @@ class Trainer:
         else:
             self.exp_avg.zero_(); self.exp_avg_sq.zero_()
             self.step_count = 0
-        self.global_step = int(ck.get("global_step", self.step_count))
+        self.global_step = max(int(ck.get("step", 0)), self.step_count)
 
     def checkpoint(self):
         """The reference's checkpoint dict (CVRP/train.py:137-141).  `optimizer_state_dict` has the layout of
@@ -162,5 +162,5 @@ class Trainer:
         group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(keys)))}
-        return {"step": self.step_count, "global_step": self.global_step, "model_state_dict": self.state_dict(),
+        return {"step": self.global_step, "model_state_dict": self.state_dict(),
                 "optimizer_state_dict": {"state": state if self.step_count > 0 else {}, "param_groups": [group]}}

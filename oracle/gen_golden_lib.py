@@ -9,6 +9,9 @@ imports this file.
     python oracle/gen_golden_lib.py cvrp           # all 100 Set-X files      (CVRP/test_vrplib.py:111-145)
     python oracle/gen_golden_lib.py cvrp X-n101-k25 X-n1001-k43
     python oracle/gen_golden_lib.py ties           # tie-order floor on X-n101 / X-n200 (see below)
+    python oracle/gen_golden_lib.py ties_tsp       # the same on lattice-like TSPLIB instances (pr107, u159, ts225, ...)
+    python oracle/gen_golden_lib.py stable_tsp     # every instance of tsplib_ref.json again with index-ordered ties
+    python oracle/gen_golden_lib.py stable_cvrp    #   -> {tsplib,setx}_ref_stable.json (summaries only)
 
 What runs is the reference's own `TSPLib_Tester.test_on_one_ins` / `VRPLib_Tester.test_on_one_ins` (imported from
 the reference tree, constructed through their own `__init__` with a checkpoint file in the reference format).  The
@@ -175,7 +178,31 @@ def _merge_json(path, rows, header):
         json.dump(dict(header, instances=sorted(old.values(), key=lambda r: (r["scale"], r["instance"]))), f, indent=0)
 
 
-def worker_cvrp(names):
+class _StableTies:
+    """Context: inside the reference's `models` module (and for Tensor.topk with largest=False) torch.topk is replaced by
+    a STABLE sort, i.e. equal distances keep node-index order."""
+    def __init__(self, ref_models):
+        self.m = ref_models
+
+    def __enter__(self):
+        import torch
+        self.orig = torch.Tensor.topk
+        orig = self.orig
+
+        def topk(x, k, dim=-1, largest=True, sorted=True):
+            if largest:
+                return orig(x, k, dim, largest, sorted)
+            v, i = torch.sort(x, dim=dim, descending=False, stable=True)
+            return v.narrow(dim, 0, k), i.narrow(dim, 0, k)
+        torch.Tensor.topk = topk
+        return self
+
+    def __exit__(self, *a):
+        import torch
+        torch.Tensor.topk = self.orig
+
+
+def worker_cvrp(names, stable=False):
     import numpy as np
     import torch
     config, sd = _setup("cvrp")
@@ -198,6 +225,10 @@ def worker_cvrp(names):
     np.savez_compressed(os.path.join(OUT, "setx_inputs.npz"), **inputs)
     header = dict(source="CVRP/test_vrplib.py:111-145 (unmodified, CPU)", seed=SEED, wseed=WSEED, gain=GAIN,
                   wsum=state_dict_checksum(sd), torch=torch.__version__)
+    if stable:
+        return _run_stable("cvrp", names, drv, ref_models, tester, header, "setx",
+                           lambda nm: dict(instance=os.path.join(base, nm + ".vrp"), solution=os.path.join(base, nm + ".sol")),
+                           lambda nm: float(inputs[nm + "/capopt"][1]))
     for nm in (names or allnames):
         detail = DETAIL.get(nm)
         got, st_rec, restore = _capture(drv, ref_models, tester, detail)
@@ -216,7 +247,28 @@ def worker_cvrp(names):
         print("%-14s N=%4d T=%4d best=%9.0f gap=%.4f  %.1fs" % (nm, row["scale"], row["T"], row["best_cost"], row["gap"], secs), flush=True)
 
 
-def worker_tsp(names):
+def _run_stable(problem, names, drv, ref_models, tester, header, kind, make_args, optimum):
+    """The instances already in <kind>_ref.json once more with index-ordered ties -> <kind>_ref_stable.json."""
+    import torch
+    with open(os.path.join(OUT, kind + "_ref.json")) as f:
+        todo = [r["instance"] for r in json.load(f)["instances"]]
+    header = dict(header, source=header["source"].replace("unmodified", "torch.topk -> stable sort: index-ordered distance ties"))
+    for nm in (names or todo):
+        got, _, restore = _capture(drv, ref_models, tester, None)
+        res = {}
+        random.seed(SEED)
+        t0 = time.time()
+        with torch.no_grad(), _StableTies(ref_models):
+            tester.test_on_one_ins(name=nm, result_dict=res, **make_args(nm))
+        secs = time.time() - t0
+        restore()
+        row = _summ(nm, res, got, secs)
+        row["optimal"] = optimum(nm)
+        _merge_json(os.path.join(OUT, kind + "_ref_stable.json"), [row], header)
+        print("%-14s N=%4d best=%10.0f gap=%.4f  %.1fs (index-ordered ties)" % (nm, row["scale"], row["best_cost"], row["gap"], secs), flush=True)
+
+
+def worker_tsp(names, stable=False):
     import numpy as np
     import torch
     config, sd = _setup("tsp")
@@ -239,6 +291,9 @@ def worker_tsp(names):
     np.savez_compressed(os.path.join(OUT, "tsplib_inputs.npz"), **inputs)
     header = dict(source="TSP/test_tsplib.py:126-162 (unmodified, CPU)", seed=SEED, wseed=WSEED, gain=GAIN,
                   wsum=state_dict_checksum(sd), torch=torch.__version__)
+    if stable:
+        return _run_stable("tsp", names, drv, ref_models, tester, header, "tsplib", lambda nm: dict(instance=data[nm]),
+                           lambda nm: float(data[nm][1]))
     for nm in (names or allnames):
         detail = DETAIL.get(nm)
         got, st_rec, restore = _capture(drv, ref_models, tester, detail)
@@ -257,16 +312,23 @@ def worker_tsp(names):
         print("%-10s N=%4d best=%10.0f gap=%.4f  %.1fs" % (nm, row["scale"], row["best_cost"], row["gap"], secs), flush=True)
 
 
-def worker_ties(names):
+def worker_ties(names, problem="cvrp"):
     """Unmodified reference vs the reference with index-ordered ties (stable sort instead of torch.topk)."""
     import numpy as np
     import torch
-    config, sd = _setup("cvrp")
+    config, sd = _setup(problem)
     from elg_b200.synth import state_dict_checksum
     import models as ref_models
-    import test_vrplib as drv
-    tester = drv.VRPLib_Tester(config)
-    base = os.path.join(REF, "CVRP", "VRPLib", "Vrp-Set-X")
+    if problem == "cvrp":
+        import test_vrplib as drv
+        tester = drv.VRPLib_Tester(config)
+        base = os.path.join(REF, "CVRP", "VRPLib", "Vrp-Set-X")
+        default = ["X-n101-k25", "X-n200-k36"]
+    else:
+        import test_tsplib as drv
+        tester = drv.TSPLib_Tester(config)
+        base = os.path.join(REF, "TSP", "TSPLib")
+        default = ["eil76", "pr107", "u159", "ts225", "a280", "pcb442"]
 
     class _StableTopk:
         """`torch` stand-in for the reference's models module: topk(largest=False) by stable sort."""
@@ -279,7 +341,7 @@ def worker_ties(names):
             v, i = torch.sort(x, dim=dim, descending=False, stable=True)
             return v.narrow(dim, 0, k), i.narrow(dim, 0, k)
 
-    for nm in (names or ["X-n101-k25", "X-n200-k36"]):
+    for nm in (names or default):
         runs = {}
         for mode in ("unmodified", "stable"):
             if mode == "stable":
@@ -290,8 +352,14 @@ def worker_ties(names):
             got, _, restore = _capture(drv, ref_models, tester, None)
             res = {}
             random.seed(SEED)
-            tester.test_on_one_ins(name=nm, result_dict=res, instance=os.path.join(base, nm + ".vrp"),
-                                   solution=os.path.join(base, nm + ".sol"))
+            with torch.no_grad():
+                if problem == "cvrp":
+                    tester.test_on_one_ins(name=nm, result_dict=res, instance=os.path.join(base, nm + ".vrp"),
+                                           solution=os.path.join(base, nm + ".sol"))
+                else:
+                    with open(os.path.join(base, nm + ".pkl"), "rb") as fh:
+                        inst = pickle.load(fh)
+                    tester.test_on_one_ins(name=nm, result_dict=res, instance=inst)
             restore()
             if mode == "stable":
                 ref_models.torch = torch
@@ -307,17 +375,25 @@ def worker_ties(names):
         np.savez_compressed(os.path.join(OUT, "ties_%s.npz" % nm),
                             tours_unmodified=ta.numpy().astype(np.int16), reward_unmodified=runs["unmodified"][1].numpy(),
                             tours_stable=tb.numpy().astype(np.int16), reward_stable=runs["stable"][1].numpy(),
-                            perm=ta[0, :, 1].numpy().astype(np.int16),
-                            meta=np.array(json.dumps(dict(name=nm, seed=SEED, wseed=WSEED, gain=GAIN,
+                            perm=ta[0, :, 1 if problem == "cvrp" else 0].numpy().astype(np.int16),
+                            meta=np.array(json.dumps(dict(name=nm, seed=SEED, wseed=WSEED, gain=GAIN, problem=problem,
+                                                          best_unmodified=float(runs["unmodified"][2]), best_stable=float(runs["stable"][2]),
                                                           wsum=state_dict_checksum(sd), rows_identical=float(same.float().mean())))))
 
 
 def main():
     if len(sys.argv) >= 3 and sys.argv[1] == "--worker":
-        {"cvrp": worker_cvrp, "tsp": worker_tsp, "ties": worker_ties}[sys.argv[2]](sys.argv[3:])
+        if sys.argv[2] == "ties_tsp":
+            worker_ties(sys.argv[3:], "tsp")
+        elif sys.argv[2] == "stable_tsp":
+            worker_tsp(sys.argv[3:], stable=True)
+        elif sys.argv[2] == "stable_cvrp":
+            worker_cvrp(sys.argv[3:], stable=True)
+        else:
+            {"cvrp": worker_cvrp, "tsp": worker_tsp, "ties": worker_ties}[sys.argv[2]](sys.argv[3:])
         return
     mode = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for m in (["tsp", "cvrp", "ties"] if mode == "all" else [mode]):
+    for m in (["tsp", "cvrp", "ties", "ties_tsp"] if mode == "all" else [mode]):
         subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", m] + sys.argv[2:], check=True)
 
 

@@ -159,7 +159,8 @@ def test_reference_style_state_drives_our_model(kind):
     while not done:
         ninf = torch.zeros(B, M, prob.xy.shape[1], device=dev).masked_fill(st.masked, float("-inf"))
         rs = _RefStyleState(selected_count=st.count, load=getattr(st, "load", None), current_node=st.cur, ninf_mask=ninf,
-                            finished=getattr(st, "finished", None))
+                            finished=getattr(st, "finished", None),
+                            BATCH_IDX=torch.arange(B, device=dev)[:, None].expand(B, M), POMO_IDX=torch.arange(M, device=dev)[None, :].expand(B, M))
         if kind == "cvrp":
             sel, _ = model.one_step_rollout(rs, None, None, None, norm_demand=None, eval_type="greedy")
             done = O.cvrp_env_step(prob, st, sel)

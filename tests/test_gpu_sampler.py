@@ -60,7 +60,7 @@ def test_sample_frequencies_follow_oracle_softmax(case, t):
         min_prob = min(min_prob, float(pr.min()))
     counts = counts.cpu()
     n = REPL * CALLS
-    assert worst_p < 1e-5, worst_p
+    assert worst_p < 5e-4, worst_p                                    # |dp| <= p |dlogit|, logits agree to ~1e-3 at worst
     assert min_prob > 0.0                                             # a zero-probability node is never drawn
     assert float(counts[masked[0]].sum()) == 0.0                      # masked nodes in particular
     # chi-square per row over the nodes with expected count >= 5 (the rest pooled into one bin)
@@ -72,7 +72,11 @@ def test_sample_frequencies_follow_oracle_softmax(case, t):
             continue                                                  # (almost) deterministic row: nothing to test
         obs = torch.cat((counts[m][big], counts[m][~big].sum()[None]))
         exp = torch.cat((e[big], e[~big].sum()[None]))
-        keep = exp > 0
+        keep = exp >= 5                                               # the pooled rare nodes only if the pool itself is large enough
+        if float(exp[-1]) < 5:                                        # otherwise a Poisson tail bound on the pool: P(X >= obs) > 1e-7
+            lam, k = float(exp[-1]), int(obs[-1])
+            tail = 1.0 - sum(math.exp(-lam) * lam ** i / math.factorial(i) for i in range(k))
+            assert k == 0 or tail > 1e-7, (m, lam, k, tail)
         chi2 = float((((obs - exp) ** 2)[keep] / exp[keep]).sum())
         df = int(keep.sum()) - 1
         # Wilson-Hilferty: chi2 is below this bound with probability 1 - 3e-6 per row
