@@ -16,7 +16,7 @@ FLAG_ENSEMBLE, FLAG_DISTANCE_PENALTY, FLAG_POSITIONAL = 1, 2, 4
 FLAG_ATTN_FP32, FLAG_ATTN_TENSOR = 8, 16
 MAX_LAYERS = 16
 NBR_STRIDE = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ModelDesc(C.Structure):
@@ -39,7 +39,7 @@ class WeightLayout(C.Structure):
 
 
 class Tables(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("xy", "demand", "unscaled", "enc", "k", "v", "e", "eb", "qtab", "qfirst", "nbr")]
+    _fields_ = [(n, C.c_void_p) for n in ("xy", "demand", "unscaled", "enc", "k", "v", "e", "eb", "qtab", "qfirst", "nbr", "et", "ws")]
 
 
 # name -> (restype, argtypes); every symbol include/elg_b200.h declares
@@ -59,6 +59,8 @@ SYMBOLS = {
     "elg_rollout_resident": (_I, [C.POINTER(ModelDesc), _I]),
     "elg_nbr_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
     "elg_e_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
+    "elg_et_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I]),
+    "elg_rollout_ws_bytes": (_SZ, [C.POINTER(ModelDesc), _I, _I, _I]),
     "elg_rollout": (_I, [C.POINTER(ModelDesc), _P, C.POINTER(Tables), _I, _I, _I, _P, _I, _U64, _I, _P, _P, _P, _P, _P, _P]),
     "elg_decode_step": (_I, [C.POINTER(ModelDesc), _P, C.POINTER(Tables), _I, _I, _I, _P, _P, _P, _P, _I, _U64, _U64,
                              _P, _P, _P, _P]),

@@ -347,6 +347,44 @@ __global__ void __launch_bounds__(256) split_kv_kernel(const float* __restrict__
   }
 }
 
+// ---- the same operands in tiles of ELG_TILE_NODES nodes for the streamed tensor-core rollout (rollout_stc.cu) ----------
+// One CTA per (aug-instance, tile): [E' | K' | V^T], each 32 KB hi + 32 KB lo, in the layouts above with N1p = 128.
+// E' is read back from the XOR-swizzled fp32 copy the fp32-pipe kernel uses (elg_tables.e); keys past N1 are zero.
+__global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restrict__ K, const float* __restrict__ V,
+                                                          const float* __restrict__ Esw, uint8_t* __restrict__ et, int N1) {
+  const int tiles = (N1 + ELG_TILE_NODES - 1) / ELG_TILE_NODES;
+  const size_t b = blockIdx.x / tiles;
+  const int tile = blockIdx.x % tiles, j0 = tile * ELG_TILE_NODES;
+  uint8_t* out = et + (size_t)blockIdx.x * ELG_TILE_BYTES;
+  for (int i = threadIdx.x; i < ELG_TILE_NODES * (E / 2); i += 256) {      // E', K': column pairs of one node -> one 32-bit word
+    const int jl = i / (E / 2), c = (i % (E / 2)) * 2, j = j0 + jl;
+    float2 ev = make_float2(0.f, 0.f), kv = make_float2(0.f, 0.f);
+    if (j < N1) {
+      const float* er = Esw + (b * N1 + j) * E;
+      ev = make_float2(er[eswz(j, c)], er[eswz(j, c + 1)]);
+      kv = *reinterpret_cast<const float2*>(K + (b * N1 + j) * E + c);
+    }
+    const uint32_t off = umma::elem_off(jl, c, ELG_TILE_NODES * 16u);
+    __half h0, l0, h1, l1;
+    umma::split_f16(ev.x, h0, l0); umma::split_f16(ev.y, h1, l1);
+    *reinterpret_cast<uint32_t*>(out + off) = umma::pack_h2(h0, h1);
+    *reinterpret_cast<uint32_t*>(out + 32768 + off) = umma::pack_h2(l0, l1);
+    umma::split_f16(kv.x, h0, l0); umma::split_f16(kv.y, h1, l1);
+    *reinterpret_cast<uint32_t*>(out + 65536 + off) = umma::pack_h2(h0, h1);
+    *reinterpret_cast<uint32_t*>(out + 65536 + 32768 + off) = umma::pack_h2(l0, l1);
+  }
+  for (int i = threadIdx.x; i < (ELG_TILE_NODES / 2) * E; i += 256) {      // V^T: node pairs of one (head, d) -> one 32-bit word
+    const int c = i % E, jl = (i / E) * 2, j = j0 + jl;
+    const float a = j < N1 ? V[(b * N1 + j) * E + c] : 0.f;
+    const float bq = j + 1 < N1 ? V[(b * N1 + j + 1) * E + c] : 0.f;
+    __half h0, l0, h1, l1;
+    umma::split_f16(a, h0, l0); umma::split_f16(bq, h1, l1);
+    const uint32_t off = (uint32_t)(c >> 4) * (ELG_TILE_NODES * 32u) + umma::elem_off(c & 15, jl, 256u);
+    *reinterpret_cast<uint32_t*>(out + 131072 + off) = umma::pack_h2(h0, h1);
+    *reinterpret_cast<uint32_t*>(out + 131072 + 32768 + off) = umma::pack_h2(l0, l1);
+  }
+}
+
 // ---- tcgen05 GEMM  C[M][N] = A[M][K] * W[N][K]^T (+ bias / relu / residual) ---------------------------------
 // Split precision: x = hi + lo (fp16 pair, ~22 mantissa bits); D = A_hi W_hi + A_hi W_lo + A_lo W_hi accumulated in
 // fp32 in TMEM (two accumulators: hi*hi | cross terms; fp32-matmul-grade accuracy, tools/umma_precision_experiment.py)
@@ -695,6 +733,11 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
     ELG_LAUNCH_OK();
   } else {
     ELG_TRY(gemm<EPI_SWIZZLE>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
+    if (t->et) {
+      split_tiles_kernel<<<(unsigned)(B * ((N1 + ELG_TILE_NODES - 1) / ELG_TILE_NODES)), 256, 0, st>>>(
+          t->k, t->v, reinterpret_cast<const float*>(t->e), reinterpret_cast<uint8_t*>(t->et), N1);
+      ELG_LAUNCH_OK();
+    }
   }
   ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 2LL * E * E, t->qtab, nullptr, nullptr, rows, E, E, E, st));
   if (d->problem == ELG_TSP)

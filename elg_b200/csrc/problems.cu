@@ -268,6 +268,11 @@ size_t elg_e_bytes(const elg_model_desc* d, int B, int N1) {
   return (size_t)B * N1 * 128 * sizeof(float);
 }
 
+size_t elg_et_bytes(const elg_model_desc* d, int B, int N1) {
+  if (check_desc(d) || B <= 0 || N1 <= 1 || rollout_is_resident(d, N1)) return 0;
+  return (size_t)B * ((N1 + ELG_TILE_NODES - 1) / ELG_TILE_NODES) * ELG_TILE_BYTES;
+}
+
 size_t elg_nbr_bytes(const elg_model_desc* d, int B, int N1) {
   if (check_desc(d) || B <= 0 || N1 <= 1) return 0;
   if (rollout_is_resident(d, N1)) return (size_t)B * N1 * ELG_NBR_NODE_BYTES(N1);

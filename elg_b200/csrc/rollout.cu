@@ -1031,6 +1031,8 @@ static int make_plan(const elg_model_desc* d, int B, int M, int N1, Plan& p) {
 
 int launch_rollout_tc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st);
 int rollout_tc_tiles(const elg_model_desc* d, int B, int M, int N1, int* mt_out);
+int launch_rollout_stc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st);      // rollout_stc.cu: large instances, streamed tiles
+bool rollout_stc_eligible(const elg_model_desc* d, const RolloutArgs& a);
 
 // Tensor-core attention kernel (rollout_tc.cu): resident instances, greedy decoding, and enough aug-instances that
 // whole-instance CTAs fill the machine -- or when forced by ELG_FLAG_ATTN_TENSOR; ELG_FLAG_ATTN_FP32 forces this file's kernel.
@@ -1046,6 +1048,7 @@ static bool use_tensor_attention(const elg_model_desc* d, const RolloutArgs& a) 
 
 static int launch_rollout(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) {
   if (use_tensor_attention(d, a)) return launch_rollout_tc(d, a, st);
+  if (rollout_stc_eligible(d, a)) return launch_rollout_stc(d, a, st);
   Plan p;
   int rc = make_plan(d, a.B, a.M, a.N1, p);
   if (rc) return rc;

@@ -45,6 +45,23 @@ struct RolloutArgs {
   float* out_logits;
 };
 
+// ---- streamed tensor-core rollout (rollout_stc.cu): tiles of elg_tables.et and the scratch elg_tables.ws ------------
+constexpr int STC_TILE = ELG_TILE_NODES;       // nodes per tile
+__host__ __device__ inline int stc_tiles(int N1) { return (N1 + STC_TILE - 1) / STC_TILE; }
+struct StcWs {
+  size_t mask, vis, nb, sc, total;      // byte offsets: three bit masks [rows][Wp] uint32, neighbour scores [rows][NP] fp32
+  int Wp, NP;                           // mask words per row (4 per tile), padded node count
+};
+__host__ __device__ inline StcWs stc_ws_layout(long long rows, int N1) {
+  StcWs w;
+  w.Wp = stc_tiles(N1) * 4;
+  w.NP = stc_tiles(N1) * STC_TILE;
+  const size_t mb = (size_t)rows * w.Wp * 4;
+  w.mask = 0; w.vis = mb; w.nb = 2 * mb; w.sc = 3 * mb;
+  w.total = 3 * mb + (size_t)rows * w.NP * 4;
+  return w;
+}
+
 // ---- small PTX helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {

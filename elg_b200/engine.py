@@ -133,8 +133,12 @@ class EncodedBatch:
         self.nbr = torch.empty(int(lib.elg_nbr_bytes(handle.desc, B, N1)),
                                dtype=torch.uint8, device=dev)
         self._big = big
+        # large instances: the operands once more as tcgen05 tiles for the streamed tensor-core rollout (0 bytes if resident)
+        n_et = int(lib.elg_et_bytes(handle.desc, B, N1))
+        self.et = torch.empty(n_et, dtype=torch.uint8, device=dev) if n_et else None
+        self.ws = None
         self.tables = _lib.Tables(*[_ptr(x).value for x in (self.xy, self.demand, self.unscaled, self.enc, self.k, self.v,
-                                                             self.e, self.eb, self.qtab, self.qfirst, self.nbr)])
+                                                             self.e, self.eb, self.qtab, self.qfirst, self.nbr, self.et, None)])
 
 
 _workspace = {}
@@ -215,6 +219,13 @@ def rollout(batch, M, start_nodes, mode="greedy", seed=0, sync_tours=True):
     reward = torch.empty((B, M), dtype=torch.float32, device=dev)
     n_steps = torch.zeros(B * tiles + 1, dtype=torch.int32, device=dev)      # last slot = work counter
     logp = torch.empty((B, M), dtype=torch.float32, device=dev) if mode == "sample" else None
+    n_ws = int(lib.elg_rollout_ws_bytes(h.desc, B, M, N1)) if (batch.et is not None and mode == "greedy") else 0
+    if n_ws:
+        if batch.ws is None or batch.ws.numel() < n_ws:
+            batch.ws = torch.empty(n_ws, dtype=torch.uint8, device=dev)
+        batch.tables.ws = batch.ws.data_ptr()
+    else:
+        batch.tables.ws = None
     with torch.cuda.device(dev):
         if profile_events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ELG_ABI_VERSION 2   /* 2: training path, data generators */
+#define ELG_ABI_VERSION 3   /* 2: training path, data generators; 3: elg_tables.et / .ws (streamed tensor-core decode) */
 
 enum { ELG_TSP = 0, ELG_CVRP = 1 };
 enum { ELG_GREEDY = 0, ELG_SAMPLE = 1 };
@@ -114,7 +114,16 @@ typedef struct elg_tables {
                                uint8 [ELG_NBR_STRIDE] list, 8-way interleaved, then float2 [N1] (distance, angle) to every node,
                                then float4 [N1] per list entry in rank order: (distance, angle, demand, node id bits)
                              larger:                       uint16 [B][N1][ELG_NBR16_STRIDE(NL)], rank order  */
+  void* et;               /* streaming variant only, may be NULL: K' / V / E' once more as tcgen05 B operands in tiles of
+                             ELG_TILE_NODES nodes, [B][tiles][E' | K' | V^T][hi | lo], ELG_TILE_BYTES per tile
+                             (elg_et_bytes() per batch); written by elg_encode when non-NULL; with it (and ws) greedy
+                             rollouts of large instances run on the streamed tensor-core kernel (rollout_stc.cu)          */
+  void* ws;               /* scratch of that kernel, elg_rollout_ws_bytes(): per-row bit masks (masked / visited /
+                             neighbour) and per-row scores of the neighbour nodes; contents need not be preserved        */
 } elg_tables;
+
+#define ELG_TILE_NODES 128                          /* nodes per operand tile of elg_tables.et        */
+#define ELG_TILE_BYTES (3 * 65536)                  /* E' | K' | V^T, 32 KB hi + 32 KB lo each        */
 
 #define ELG_NBR_STRIDE 128                          /* list bytes per node, resident variant          */
 #define ELG_NBR_PAIR_BYTES(N1) (8 * (((N1) + 1) & ~1))                     /* pair features indexed by node id       */
@@ -175,6 +184,8 @@ int elg_rollout_tiles(const elg_model_desc* desc, int B, int M, int N1);
 int elg_rollout_resident(const elg_model_desc* desc, int N1);   /* 1 = resident variant, 0 = streaming, <0 = error */
 size_t elg_nbr_bytes(const elg_model_desc* desc, int B, int N1);
 size_t elg_e_bytes(const elg_model_desc* desc, int B, int N1);
+size_t elg_et_bytes(const elg_model_desc* desc, int B, int N1);              /* 0 for resident instances */
+size_t elg_rollout_ws_bytes(const elg_model_desc* desc, int B, int M, int N1);   /* 0 for resident instances */
 int elg_rollout(const elg_model_desc* desc, const float* derived, const elg_tables* t, int B, int M, int N1,
                 const int32_t* start_nodes, int mode, uint64_t seed, int t_max, int16_t* tours, float* reward,
                 int32_t* n_steps, float* logp, int32_t* work_counter, void* stream);

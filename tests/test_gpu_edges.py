@@ -53,6 +53,41 @@ def test_ragged_shapes_match_oracle(kind, N, M, n, aug):
 
 
 @pytest.mark.parametrize("kind,N,M,n,aug", [
+    ("cvrp", 112, 9, 1, 1),     # N+1 = 113: one key tile with 113 live keys, one row tile with 9 live rows
+    ("cvrp", 128, 40, 1, 8),    # N+1 = 129: the second key tile holds a single node
+    ("cvrp", 200, 130, 1, 1),   # two row tiles (128 + 2 rows), two key tiles
+    ("cvrp", 300, 64, 1, 8),    # three key tiles, neighbour lists of more than two 128-entry chunks late in the rollout
+    ("tsp", 113, 7, 1, 1),
+    ("tsp", 129, 129, 1, 1),    # 2 row tiles, 2 key tiles
+    ("tsp", 260, 50, 1, 8),
+])
+def test_ragged_shapes_streamed_tensor_core_kernel(kind, N, M, n, aug):
+    """Large instances on the streamed tensor-core kernel (rollout_stc.cu; attention = auto) against the oracle."""
+    tours, reward, ref_t, ref_r, prob = _run(kind, N, M, n, aug, attention="auto")
+    frac, same = compare_tours(tours, ref_t)
+    assert frac >= 0.9, frac
+    assert ((reward - ref_r).abs() / ref_r.abs())[same].max() < 1e-4
+    if kind == "cvrp":
+        O.check_feasible_cvrp(tours, prob.demand)
+    else:
+        assert torch.equal(tours.sort(dim=2)[0], torch.arange(N).expand_as(tours))
+
+
+def test_streamed_kernel_is_the_one_that_runs():
+    """The dispatch really takes the streamed tensor-core kernel for a large greedy rollout: same tours as the fp32-pipe
+    kernel, and the scratch it needs was requested."""
+    from elg_b200 import _lib, engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS
+    desc = engine.make_desc("cvrp", dict(DEFAULT_MODEL_PARAMS["cvrp"]))
+    assert int(_lib.lib.elg_et_bytes(desc, 8, 201)) == 8 * 2 * 3 * 65536
+    assert int(_lib.lib.elg_rollout_ws_bytes(desc, 8, 200, 201)) > 0 and int(_lib.lib.elg_rollout_ws_bytes(desc, 8, 100, 101)) == 0
+    a = _run("cvrp", 150, 60, 1, 8, attention="auto")
+    b = _run("cvrp", 150, 60, 1, 8, attention="fp32")
+    frac, _ = compare_tours(a[0], b[0])
+    assert frac >= 0.97, frac
+
+
+@pytest.mark.parametrize("kind,N,M,n,aug", [
     ("cvrp", 5, 1, 3, 1),       # N+1 = 6 -> one 16-column MMA tile, one live TMEM lane
     ("cvrp", 7, 5, 2, 8),
     ("cvrp", 15, 15, 2, 8),     # N+1 = 16: no padded key columns

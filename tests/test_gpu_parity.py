@@ -31,13 +31,16 @@ def _setup(g, attention="fp32"):
 
 
 def _case_params():
-    """Every fixture on the fp32-pipe attention kernel; the resident ones (N+1 <= 112) also on the tensor-core kernel."""
+    """Every fixture on the fp32-pipe attention kernel; the resident ones (N+1 <= 112) also on the tensor-core kernel, the
+    larger ones also on the streamed tensor-core kernel."""
     out = []
     for name in ALL_CASES:
         out.append((name, "fp32"))
         g = Golden(name)
         if g.meta["N"] + (1 if g.kind == "cvrp" else 0) <= 112:
             out.append((name, "tensor"))
+        else:
+            out.append((name, "auto"))      # large instances: the streamed tensor-core kernel (rollout_stc.cu) does the rollout
     return out
 
 
