@@ -53,8 +53,9 @@ struct StcL {      // shared-memory layout in floats (compile-time)
   static constexpr int xch = addid + 128 * SKT / 2;              // [4][128] float4: validity words / denominators
   static constexpr int xm = xch + 4 * 128 * 4;                   // [4][128] float2: maxima / arg-max candidates
   static constexpr int eb = xm + 4 * 128 * 2;                    // [2][128] score bias of the current node tiles
-  static constexpr int ctrl = eb + 256;
-  static constexpr int bar = ctrl + 4;                           // 8 mbarriers + TMEM base address
+  static constexpr int dem = eb + 256;                           // demands of the instance when N+1 <= 4096 (phase C)
+  static constexpr int ctrl = dem + 4096;
+  static constexpr int bar = ctrl + 4;                           // 9 mbarriers + TMEM base address
   static constexpr int total = bar + 20;
 };
 static_assert(StcL::total * 4 <= 227 * 1024, "layout exceeds one SM's shared memory");
@@ -109,12 +110,13 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
   float2* sX2 = reinterpret_cast<float2*>(sm + L::xm);
   float* sEb = sm + L::eb;
   int* sCtrl = reinterpret_cast<int*>(sm + L::ctrl);
-  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sm + L::bar);   // TMA: K' + V^T tile
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sm + L::bar);   // TMA: K' tile
   uint64_t* bar_e = bar_kv + 1;                                   // [2] TMA: E' tiles
   uint64_t* bar_scm = bar_kv + 3;                                 // [2] tcgen05.commit of the score tiles
   uint64_t* bar_g = bar_kv + 5;                                   // [2] tcgen05.commit of the softmax groups
   uint64_t* bar_loc = bar_kv + 7;                                 // tcgen05.commit of the local-policy MMAs
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_kv + 8);
+  uint64_t* bar_v = bar_kv + 8;                                   // TMA: V^T tile
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_kv + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, wsub = warp >> 2, grp = wsub >> 1, kh = wsub & 1;
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
     }
     for (int i = tid; i < N2 * LE; i += RT) w[L::op2 + i] = loc[LOC_OP2 + i];
     if (tid == 0) {
-      for (int i = 0; i < 8; ++i) mbar_init(bar_kv + i, 1);
+      for (int i = 0; i < 9; ++i) mbar_init(bar_kv + i, 1);
+      sCtrl[1] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) umma::tmem_alloc(tmem_ptr, 512);
@@ -158,8 +161,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
 
   const int tiles_m = (A.M + 127) >> 7;
   const int total_work = A.B * tiles_m;
-  uint32_t ph_kv = 0, ph_e[2] = {0, 0}, ph_sc[2] = {0, 0}, ph_grp = 0;      // mbarrier parities
+  uint32_t ph_kv = 0, ph_v = 0, ph_e[2] = {0, 0}, ph_sc[2] = {0, 0}, ph_grp = 0;      // mbarrier parities
   const bool leader = tid == grp * 256;
+#ifdef ELG_PHASE_TIMING
+  unsigned long long pclk[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
   for (;;) {
     if (tid == 0) sCtrl[0] = atomicAdd(A.work_counter, 1);
@@ -180,6 +186,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
     const float* pDem = CVRP ? A.t.demand + (size_t)b * N1 : nullptr;
     const float* pEb = A.t.eb + (size_t)b * N1;
 
+    if (CVRP && N1 <= 4096)
+      for (int i = tid; i < N1; i += RT) (sm + L::dem)[i] = pDem[i];
+    const float* cDem = (CVRP && N1 <= 4096) ? sm + L::dem : pDem;       // phase C compares every demand with the load
     if (tid < 128) {
       sCur[tid] = 0; sFirst[tid] = 0; sLoad[tid] = 1.f; sTlen[tid] = 0.f; sCnt[tid] = 0; sNp[tid] = 0;
       sFin[tid] = tid < nrows ? 0 : 1;
@@ -196,14 +205,16 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
       const bool act = in_tile && !sFin[row];
       const int cnt0 = sCnt[row];
       int sl = 0;
+      PHASE_T0();
 
       if (!forced) {
         // ---- K' / V^T of key tile 0 on their way while the local policy runs ---------------------------------------
         if (tid == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(bar_kv, 131072u);
+          mbar_expect_tx(bar_kv, 65536u);
           bulk_g2s(sm + L::buf, et + 65536, 65536u, bar_kv);
-          bulk_g2s(sm + L::buf + 16384, et + 131072, 65536u, bar_kv);
+          mbar_expect_tx(bar_v, 65536u);
+          bulk_g2s(sm + L::buf + 16384, et + 131072, 65536u, bar_v);
         }
         // ---- Q operand ----------------------------------------------------------------------------------------------
         {
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           umma::st16s<1>(tl + SC_Q + 16 * wsub, hw);
           umma::st16s<1>(tl + SC_Q + 64 + 16 * wsub, lw);
         }
+        PHASE_MARK(0);
 
         // =================== L: local policy ===========================================================================
         // (1) the first k valid entries of the rank-ordered neighbour list of `cur`, 128 entries at a time: this thread
@@ -299,6 +311,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           if (!more) break;
         }
         const int kk = min(c0, kloc);
+        PHASE_MARK(1);
         const int np = act ? kk + DEP : 0;
         // slot s of this thread is sequence position p0 + s; neighbour rank p0 + s - DEP (the depot heads the cvrp sequence)
         float f0[SPT], f1[SPT], f2[SPT];
@@ -337,6 +350,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           if (DEP && wsub == 0 && np > 0) atomicOr(gnb, 1u);
         }
         const bool depot_masked = CVRP && act && (gmask[0] & 1u);
+        PHASE_MARK(2);
         const int nv = np - p0;
         const bool dep_off = DEP && wsub == 0 && depot_masked;
         auto load_head = [&](int h, float4& u, float (&tq)[SPT]) {
@@ -418,6 +432,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           }
           umma::commit(bar_loc);
         }
+        PHASE_MARK(3);
         mbar_wait(bar_loc, 0u);
         umma::fence_after_sync();
         {
@@ -485,6 +500,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
             umma::mma_f16_ts(d, aHi + 8 * ks, umma::make_desc(op2 + ks * 2 * lbo2, lbo2, 128), idescL2, true);
           umma::commit(bar_loc);
         }
+        PHASE_MARK(4);
         // (6) penalty + local score per sequence position -> shared memory (with the node ids), read back after the score tiles
         mbar_wait(bar_loc, 1u);
         umma::fence_after_sync();
@@ -514,6 +530,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
         umma::fence_before_sync();
         __syncthreads();                       // [pem | z] read by everybody before the first P V reuses the columns
 
+        PHASE_MARK(5);
         // =================== global policy: online softmax over the key tiles ==========================================
         float mr0 = -INFINITY, mr1 = -INFINITY, mr2 = -INFINITY, mr3 = -INFINITY;      // running maxima of heads 4 grp + rho
         float lt0 = 0.f, lt1 = 0.f, lt2 = 0.f, lt3 = 0.f;                               // running denominators (my key half)
@@ -527,12 +544,6 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
             v0 = ~mw.x & (n0 >= 32 ? FULL : (n0 > 0 ? ((1u << n0) - 1u) : 0u));
             v1 = ~mw.y & (n1 >= 32 ? FULL : (n1 > 0 ? ((1u << n1) - 1u) : 0u));
           }
-          if (kt > 0 && tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar_kv, 131072u);
-            bulk_g2s(sm + L::buf, et + (size_t)kt * ELG_TILE_BYTES + 65536, 65536u, bar_kv);
-            bulk_g2s(sm + L::buf + 16384, et + (size_t)kt * ELG_TILE_BYTES + 131072, 65536u, bar_kv);
-          }
           if (leader) {
             mbar_wait(bar_kv, ph_kv);
             umma::fence_after_sync();
@@ -545,6 +556,15 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
             mbar_wait(bar_grp, ph_grp);
             ph_grp ^= 1;
             umma::fence_after_sync();
+            if (rho == 3 && leader && kt + 1 < NT) {
+              // the K' tile has been read for the last time by this group; the second leader to get here refills it
+              if (atomicAdd(&sCtrl[1], 1) == 1) {
+                sCtrl[1] = 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar_kv, 65536u);
+                bulk_g2s(sm + L::buf, et + (size_t)(kt + 1) * ELG_TILE_BYTES + 65536, 65536u, bar_kv);
+              }
+            }
             const uint32_t sb = tl + SC_S + grp * 128;
             uint32_t sr[64];
             umma::ld32_nw(sb + kh * 64, sr);
@@ -603,6 +623,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
             umma::fence_before_sync();
             group_sync_s(9 + grp);
             if (leader) {
+              if (rho == 0) mbar_wait(bar_v, ph_v);                   // the tile's V^T (in flight since the end of the previous tile)
               umma::fence_after_sync();
               issue_pv(4 * grp + rho, kt > 0);
               if (rho < 3) issue_qk(4 * grp + rho + 1);
@@ -612,10 +633,17 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           // every MMA of this tile done (both groups) before the buffers are refilled / the accumulators are read
           mbar_wait(bar_grp, ph_grp);
           ph_grp ^= 1;
+          ph_v ^= 1;
           umma::fence_after_sync();
           umma::fence_before_sync();
           __syncthreads();
+          if (tid == 0 && kt + 1 < NT) {          // V^T of the next tile; its K' has been on its way since round 3
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar_v, 65536u);
+            bulk_g2s(sm + L::buf + 16384, et + (size_t)(kt + 1) * ELG_TILE_BYTES + 131072, 65536u, bar_v);
+          }
         }
+        PHASE_MARK(6);
         // ---- E' tiles 0 and 1 on their way; O = accumulators / denominators -> O operand --------------------------------
         if (tid == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -652,6 +680,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
         }
         __syncthreads();
 
+        PHASE_MARK(7);
         // =================== score tiles: running arg-max of clip * tanh(score + eb + xi) ================================
         auto issue_score = [&](int nt) {
           const uint32_t eB = (nt & 1) ? bufB : bufA;
@@ -727,18 +756,28 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           }
           if (nt + 2 < NT || nt + 1 < NT) __syncthreads();
         }
+        PHASE_MARK(8);
         // ---- the neighbours (and the depot) with their own penalty + local score -------------------------------------------
         if (act) {
           const int npr = sNp[row];
+          int ndv[SPT];
+          float xv[SPT];
 #pragma unroll
-          for (int s = 0; s < SPT; ++s) {
+          for (int s = 0; s < SPT; ++s) {            // every load first (independent L2 round trips), then the comparisons
             const int p = p0 + s;
+            ndv[s] = -1;
+            xv[s] = 0.f;
             if (p < npr) {
               const int nd = sAddId[row * SKT + p];
               const bool masked = (gmask[nd >> 5] >> (nd & 31)) & 1u;
-              if (!masked) consider((gsc[nd] + pEb[nd]) + sAdd[row * SKT + p], nd);
-              gnb[nd >> 5] = 0u;
+              xv[s] = (gsc[nd] + pEb[nd]) + sAdd[row * SKT + p];
+              ndv[s] = masked ? -2 - nd : nd;
             }
+          }
+#pragma unroll
+          for (int s = 0; s < SPT; ++s) {
+            if (ndv[s] >= 0) consider(xv[s], ndv[s]);
+            if (ndv[s] != -1) gnb[(ndv[s] >= 0 ? ndv[s] : -2 - ndv[s]) >> 5] = 0u;
           }
         }
         sX2[wsub * 128 + row] = make_float2(vbest, __int_as_float(ibest));
@@ -758,6 +797,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
         sl = (CVRP && t == 0) ? 0 : A.start_nodes[min(row0 + row, A.M - 1)];
       }
 
+      PHASE_MARK(9);
       // ================= phase C: environment step on the global bit masks; this thread owns words w = wsub mod 4 =========
       bool live_after = false;
       if (in_tile) {
@@ -780,7 +820,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
 #pragma unroll 8
               for (int i = 0; i < 32; ++i) {
                 const int j = jb + i;
-                if (j < N1 && lde < pDem[j]) big |= 1u << i;
+                if (j < N1 && lde < cDem[j]) big |= 1u << i;
               }
             }
             uint32_t mk = vw | big;
@@ -816,7 +856,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           if (t < A.t_max) A.tours[((size_t)b * A.M + row0 + row) * A.t_max + t] = (int16_t)sl;
         }
       }
+      PHASE_MARK(10);
       bool more = __syncthreads_or(live_after ? 1 : 0) != 0;
+      PHASE_MARK(11);
       if (!CVRP) more = (t + 1) < N1;
       if (!more || t + 1 >= A.t_max) { ++t; break; }
     }
@@ -843,6 +885,10 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tm, 512);
+#ifdef ELG_PHASE_TIMING
+  if (tid == 0)
+    for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_clk[i], pclk[i]);
+#endif
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -876,3 +922,11 @@ extern "C" size_t elg_rollout_ws_bytes(const elg_model_desc* d, int B, int M, in
   if (elg::check_desc(d) || B <= 0 || M <= 0 || N1 <= elg::N_RES_MAX || N1 > elg::N_STREAM_MAX) return 0;
   return elg::stc_ws_layout((long long)B * M, N1).total;
 }
+
+#ifdef ELG_PHASE_TIMING
+extern "C" int elg_debug_phase_clocks_stc(unsigned long long* out16, int reset) {
+  ELG_CUDA_OK(cudaMemcpyFromSymbol(out16, elg::g_phase_clk, sizeof(unsigned long long) * 16));
+  if (reset) { unsigned long long z[16] = {0}; ELG_CUDA_OK(cudaMemcpyToSymbol(elg::g_phase_clk, z, sizeof(z))); }
+  return ELG_OK;
+}
+#endif
