@@ -103,13 +103,14 @@ __device__ __forceinline__ int select128(const uint32_t (&r)[4], int n) {
 }
 
 // =================================================================================================
-template <int PROBLEM, int MAXE>
+// NP = 112: the node count rounded up to 16 is known at compile time (the 100-node benchmark shapes); NP = 0: run time
+template <int PROBLEM, int MAXE, int NP>
 __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) {
   constexpr bool CVRP = PROBLEM == ELG_CVRP;
   constexpr int DEP = CVRP ? 1 : 0;
   extern __shared__ __align__(128) float sm[];
   const int N1 = A.N1;
-  const int N1p = (N1 + 15) & ~15;
+  const int N1p = NP ? NP : ((N1 + 15) & ~15);
   const int W = (N1 + 31) >> 5;
   constexpr int KT = MAXE * 8;
   const int K1 = A.k_local + DEP;
@@ -702,41 +703,29 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
                 mloc = fmaxf(mloc, s);
               }
             }
-          const float moff = mloc == -INFINITY ? 0.f : mloc - TC_P_SCALE_LOG2;
-          float lloc = 0.f;
-#pragma unroll
-          for (int c8 = 0; c8 < 7; ++c8)
-            if (c8 * 8 < KH) {
-#pragma unroll
-              for (int i = c8 * 8; i < c8 * 8 + 8; ++i) {
-                const float s = __uint_as_float(sr[i]);
-                const float p = umma::ex2_raw(s - moff);
-                lloc += p;
-                sr[i] = __float_as_uint(p);
-              }
-            }
-          // combine the two key halves of (row, head): common reference max, total denominator
+          // the row's maximum over both key halves first (shared memory + 64-thread barrier): both halves then use the same
+          // offset, no rescaling of the weights; the two partial denominators meet at the normalisation of O
           sXm[wsub * 128 + row] = mloc;
-          sXl[wsub * 128 + row] = lloc;
           pair_sync(1 + grp * 4 + q);
-          const float mo = sXm[(wsub ^ 1) * 128 + row], lo_ = sXl[(wsub ^ 1) * 128 + row];
-          const float mm = fmaxf(mloc, mo);
-          const float cown = mloc == -INFINITY ? 0.f : umma::ex2_raw(mloc - mm);
-          const float coth = mo == -INFINITY ? 0.f : umma::ex2_raw(mo - mm);
-          const float ltot = fmaf(lloc, cown, lo_ * coth);
-          if (rho == 0) lt0 = ltot; else if (rho == 1) lt1 = ltot; else if (rho == 2) lt2 = ltot; else lt3 = ltot;
+          const float mm = fmaxf(mloc, sXm[(wsub ^ 1) * 128 + row]);
+          const float moff = mm == -INFINITY ? 0.f : mm - TC_P_SCALE_LOG2;
+          float lloc = 0.f;
           // P (fp16 hi/lo, two keys per 32-bit column) in place of S: hi at [sb, sb + N1p/2), lo behind it
 #pragma unroll
           for (int c8 = 0; c8 < 7; ++c8)
             if (c8 * 8 < KH) {
 #pragma unroll
               for (int i = c8 * 4; i < c8 * 4 + 4; ++i) {       // keys (2i, 2i+1) -> hi word in sr[2i], lo word in sr[2i+1]
+                const float pa = umma::ex2_raw(__uint_as_float(sr[2 * i]) - moff);
+                const float pb = umma::ex2_raw(__uint_as_float(sr[2 * i + 1]) - moff);
+                lloc += pa + pb;
                 uint32_t hwd, lwd;
-                umma::split2_f16(__uint_as_float(sr[2 * i]) * cown, __uint_as_float(sr[2 * i + 1]) * cown, hwd, lwd);
+                umma::split2_f16(pa, pb, hwd, lwd);
                 sr[2 * i] = hwd;
                 sr[2 * i + 1] = lwd;
               }
             }
+          if (rho == 0) lt0 = lloc; else if (rho == 1) lt1 = lloc; else if (rho == 2) lt2 = lloc; else lt3 = lloc;
           umma::st_words<2>(sb + kh * (KH >> 1), sr, KH >> 1);
           umma::st_words<2>(sb + (N1p >> 1) + kh * (KH >> 1), sr + 1, KH >> 1);
           umma::wait_st();
@@ -758,12 +747,19 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         mbar_wait(bar_grp, step_par);
         umma::fence_after_sync();
         {
+          // this thread normalises heads 4*grp + 2*kh, + 1 and needs the other key half's denominators of those two heads;
+          // it publishes its own partial denominators of the two heads the partner normalises
+          sXm[wsub * 128 + row] = kh ? lt0 : lt2;
+          sXl[wsub * 128 + row] = kh ? lt1 : lt3;
+          pair_sync(1 + grp * 4 + q);
+          const float la = (kh ? lt2 : lt0) + sXm[(wsub ^ 1) * 128 + row];
+          const float lb = (kh ? lt3 : lt1) + sXl[(wsub ^ 1) * 128 + row];
           uint32_t orr[32], hw[16], lw[16];            // heads 4*grp + 2*kh, + 1: 32 consecutive accumulator columns
           umma::ld32_nw(tl + TC_COL_O + 16 * (4 * grp + 2 * kh), orr);
           umma::wait_ld();
 #pragma unroll
           for (int i2 = 0; i2 < 2; ++i2) {
-            const float lsel = kh ? (i2 ? lt3 : lt2) : (i2 ? lt1 : lt0);
+            const float lsel = i2 ? lb : la;
             const float inv_l = act ? 1.f / lsel : 0.f;
 #pragma unroll
             for (int d2 = 0; d2 < 8; ++d2)
@@ -1048,10 +1044,16 @@ int launch_rollout_tc(const elg_model_desc* d, RolloutArgs& a, cudaStream_t st) 
   ELG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int work = a.B * a.tiles;
   const int grid = work < sms ? work : sms;
+  const bool np112 = ((a.N1 + 15) & ~15) == 112;
 #define ELG_TK(P, ME)                                                                                              \
   do {                                                                                                             \
-    ELG_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<P, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    rollout_tc_kernel<P, ME><<<grid, RT, smem, st>>>(a);                                                           \
+    if (np112) {                                                                                                   \
+      ELG_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<P, ME, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      rollout_tc_kernel<P, ME, 112><<<grid, RT, smem, st>>>(a);                                                    \
+    } else {                                                                                                       \
+      ELG_CUDA_OK(cudaFuncSetAttribute(rollout_tc_kernel<P, ME, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      rollout_tc_kernel<P, ME, 0><<<grid, RT, smem, st>>>(a);                                                      \
+    }                                                                                                              \
   } while (0)
   if (d->problem == ELG_CVRP) {
     if (maxe == 4) ELG_TK(ELG_CVRP, 4); else ELG_TK(ELG_CVRP, 6);
