@@ -3,13 +3,15 @@
 
     python tools/ncu_phase_shares.py sass.csv lines.txt <mangled kernel> <source file>     (inputs as for ncu_source_lines.py)
 
-The `ranges` table below holds the phase boundaries of rollout_tc.cu at the commit profiles/r01_rollout_tc_ncu.md was
+The `ranges` table below holds the phase boundaries of rollout_tc.cu at the commit profiles/r02_rollout_tc_ncu.md was
 taken from; edit it when the file moves (grep -n PHASE_MARK gives the boundaries)."""
 import csv, re, sys
 from collections import defaultdict
 sass_csv, lines_txt, kernel, srcname = sys.argv[1:5]
-ranges = [("setup/other", 0, 235), ("step start+mask", 236, 254), ("Q build", 255, 312), ("softmax rounds", 313, 398), ("B1", 399, 614),
-          ("O operand+score issue", 615, 654), ("B3", 655, 742), ("select", 743, 765), ("phase C", 766, 836), ("epilogue", 837, 2000)]
+ranges = [("helpers / setup (inlined)", 0, 262), ("Q row + list prefetch lambdas", 263, 308), ("step start", 309, 323), ("L1 list validity + exchange", 324, 357),
+          ("L2 bit scan + records + features", 358, 432), ("L3 local scores + max/neighbour-bit exchange", 433, 491), ("L4 weights -> TMEM + MMA1", 492, 548),
+          ("L5 ol + MMA2 / first QK issue", 549, 623), ("L6 local finalize", 624, 658), ("softmax rounds", 659, 745),
+          ("O operand + score issue", 746, 791), ("B3", 792, 879), ("select", 880, 902), ("phase C", 903, 973), ("epilogue", 974, 3000)]
 cur, inside, per_instr = None, False, []
 for ln in open(lines_txt):
     if ln.startswith(".text."):
