@@ -795,6 +795,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
         }
       } else {
         sl = (CVRP && t == 0) ? 0 : A.start_nodes[min(row0 + row, A.M - 1)];
+        __syncthreads();      // forced steps have no other barrier between the row-state reads above and phase C's rewrite
       }
 
       PHASE_MARK(9);

@@ -70,8 +70,8 @@ struct TcL {
   static constexpr int tlen = load + MT;
   static constexpr int fin = tlen + MT;
   static constexpr int mask = fin + MT;                           // word-major [4][128]: bank = row % 32 whatever the word
-  static constexpr int vis = mask + 4 * 128;
-  static constexpr int add = vis + MT * 4;                       // penalty + local of each row's neighbours (stride KT), ordered by node id
+  static constexpr int vis = mask + 4 * 128;                     // two copies: a step reads one and writes the other
+  static constexpr int add = vis + 2 * MT * 4;                       // penalty + local of each row's neighbours (stride KT), ordered by node id
   static constexpr int nb = add + (MT * KT > TC_XCH_FLOATS ? MT * KT : TC_XCH_FLOATS);   // neighbour bit mask per row
   static constexpr int xch = nb + MT * 4;                        // softmax (max, sum) exchange; later the 4 argmax candidates per row
   static constexpr int ctrl = xch + 2 * 4 * 128;
@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
     for (int i = tid; i < A.MT * 4; i += RT) {
       const int r = i >> 2, w = i & 3;
       sVis[i] = 0u;
+      sVis[TC_MT_MAX * 4 + i] = 0u;
       sMask[w * 128 + r] = (A.single_step && r < nrows && w < W) ? A.st_mask[((size_t)b * A.M + row0 + r) * W + w] : 0u;
     }
     mbar_wait(bar, bar_phase);
@@ -904,7 +905,11 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         const bool was_fin = !act;
         bool fin = was_fin;
         float ld = 1.f;
-        const uint4 v4 = *reinterpret_cast<const uint4*>(sVis + rc * 4);
+        // visited words: every thread of the row reads all four, then rewrites its own -- into the other copy, so that no
+        // thread can see a word of this step before it has read the previous step's
+        const uint32_t* visR = sVis + (t & 1) * (TC_MT_MAX * 4);
+        uint32_t* visW = sVis + ((t + 1) & 1) * (TC_MT_MAX * 4);
+        const uint4 v4 = *reinterpret_cast<const uint4*>(visR + rc * 4);
         uint32_t vw[4] = {v4.x, v4.y, v4.z, v4.w};
         const uint32_t sbit = 1u << (sl & 31);
         vw[0] |= (sl >> 5) == 0 ? sbit : 0u; vw[1] |= (sl >> 5) == 1 ? sbit : 0u;
@@ -934,13 +939,13 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
             const uint32_t mine = pick4(vw, wsub);
             uint32_t mk = mine | big;
             if (wsub == 0 && fin) mk &= ~1u;               // finished rows may stay at the depot
-            sVis[rc * 4 + wsub] = mine;
+            visW[rc * 4 + wsub] = mine;
             sMask[wsub * 128 + rc] = mk;
           }
         } else {
           if (wsub < W) {
             const uint32_t mine = pick4(vw, wsub);
-            sVis[rc * 4 + wsub] = mine;
+            visW[rc * 4 + wsub] = mine;
             sMask[wsub * 128 + rc] = mine;
           }
         }
