@@ -49,7 +49,7 @@ struct RolloutArgs {
 constexpr int STC_TILE = ELG_TILE_NODES;       // nodes per tile
 __host__ __device__ inline int stc_tiles(int N1) { return (N1 + STC_TILE - 1) / STC_TILE; }
 struct StcWs {
-  size_t mask, vis, nb, sc, total;      // byte offsets: three bit masks [rows][Wp] uint32, neighbour scores [rows][NP] fp32
+  size_t mask, vis, nb, total;          // byte offsets: three bit masks [rows][Wp] uint32
   int Wp, NP;                           // mask words per row (4 per tile), padded node count
 };
 __host__ __device__ inline StcWs stc_ws_layout(long long rows, int N1) {
@@ -57,8 +57,8 @@ __host__ __device__ inline StcWs stc_ws_layout(long long rows, int N1) {
   w.Wp = stc_tiles(N1) * 4;
   w.NP = stc_tiles(N1) * STC_TILE;
   const size_t mb = (size_t)rows * w.Wp * 4;
-  w.mask = 0; w.vis = mb; w.nb = 2 * mb; w.sc = 3 * mb;
-  w.total = 3 * mb + (size_t)rows * w.NP * 4;
+  w.mask = 0; w.vis = mb; w.nb = 2 * mb;
+  w.total = 3 * mb;
   return w;
 }
 

@@ -8,7 +8,7 @@
 //     S_h = Q_h K'_h^T (N = 128)  A = Q (TMEM)    online softmax over the tiles in the log2 domain: running maximum and
 //     O_h += P_h V_h   (N = 16)   A = P (TMEM)    denominator per (row, head) in registers; when a tile raises the maximum
 //                                                 the head's 16 accumulator columns are rescaled in tensor memory first
-//   for every tile of 128 nodes:  TMA bulk copy of the E' tile (64 KB, double buffered)
+//   for every tile of 128 nodes:  TMA bulk copy of the E' tile (64 KB; the next one streams in while this one's scores are read)
 //     score = O E'^T  (N = 128)   A = O (TMEM)    running first-max arg-max of clip * tanh(score + eb + xi) over the tiles
 //
 // CTA = one (aug-instance, tile of 128 POMO rows); TMEM lane = row; 16 warps as in rollout_tc.cu (lane quadrant q =
@@ -16,8 +16,9 @@
 // The local policy (CVRP/models.py:51-175) is the TMEM-lane formulation of rollout_tc.cu with both contractions on
 // tcgen05; its neighbourhood comes from the uint16 rank-ordered neighbour lists, tested 128 entries at a time until k
 // valid ones are found, and its features (distance, polar angle, demand / load) are computed in the kernel.  The ~k
-// neighbour nodes of a row get their exact logit afterwards: while the score tiles stream by, the raw scores of flagged
-// nodes are parked in a per-row scratch line and the flagged nodes are left out of the running arg-max.
+// neighbour nodes of a row get their exact logit per tile: the scores of flagged nodes are parked in an on-chip
+// [128 rows][128 nodes] scratch (the second 64 KB buffer), left out of the running arg-max, and compared with their
+// penalty + local score by the threads that own the local sequence.
 // Per-row bit masks (masked / visited / neighbour, one 32-bit word per 32 nodes) live in global scratch (L2-resident).
 //
 // TMEM columns: [0,128) Q hi|lo, later O hi|lo   [128,256) O accumulators (8 heads x 16)
@@ -66,6 +67,7 @@ __device__ __forceinline__ uint32_t pick4s(const uint32_t (&w)[4], int i) {
 __device__ __forceinline__ void pair_sync_s(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void group_sync_s(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void quad_sync_s(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ float scr_at(const float* sSc, int row, int jl, int lane) { return sSc[row * 128 + (jl ^ lane)]; }
 __device__ __forceinline__ int select128s(const uint32_t (&r)[4], int n) {
   const int c0 = __popc(r[0]), c1 = c0 + __popc(r[1]), c2 = c1 + __popc(r[2]);
   const int w = (n >= c0 ? 1 : 0) + (n >= c1 ? 1 : 0) + (n >= c2 ? 1 : 0);
@@ -180,7 +182,6 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
     uint32_t* gmask = reinterpret_cast<uint32_t*>(wsb + WS.mask) + g * Wp;
     uint32_t* gvis = reinterpret_cast<uint32_t*>(wsb + WS.vis) + g * Wp;
     uint32_t* gnb = reinterpret_cast<uint32_t*>(wsb + WS.nb) + g * Wp;
-    float* gsc = reinterpret_cast<float*>(wsb + WS.sc) + g * WS.NP;
     const uint8_t* et = reinterpret_cast<const uint8_t*>(A.t.et) + (size_t)b * NT * ELG_TILE_BYTES;
     const float* pXY = A.t.xy + (size_t)b * N1 * 2;
     const float* pDem = CVRP ? A.t.demand + (size_t)b * N1 : nullptr;
@@ -644,19 +645,14 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
           }
         }
         PHASE_MARK(6);
-        // ---- E' tiles 0 and 1 on their way; O = accumulators / denominators -> O operand --------------------------------
+        // ---- E' tile 0 on its way; O = accumulators / denominators -> O operand -----------------------------------------
         if (tid == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_expect_tx(bar_e, 65536u);
           bulk_g2s(sm + L::buf, et, 65536u, bar_e);
-          if (NT > 1) {
-            mbar_expect_tx(bar_e + 1, 65536u);
-            bulk_g2s(sm + L::buf + 16384, et + ELG_TILE_BYTES, 65536u, bar_e + 1);
-          }
         }
         sX4[wsub * 128 + row] = make_float4(lt0, lt1, lt2, lt3);
         if (tid < 128) sEb[tid] = tid < N1 ? pEb[tid] : 0.f;
-        else if (tid < 256) sEb[tid] = tid < N1 ? pEb[tid] : 0.f;
         pair_sync_s(1 + grp * 4 + q);
         {
           const float4 lo4 = sX4[(wsub ^ 1) * 128 + row];
@@ -682,26 +678,23 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
 
         PHASE_MARK(7);
         // =================== score tiles: running arg-max of clip * tanh(score + eb + xi) ================================
+        // E' tiles come through the first 64 KB buffer (the next one is requested as soon as the tile's MMAs are done, i.e.
+        // while its scores are being read); the second buffer is a [128 rows][128 nodes] scratch for the scores of the
+        // tile's NEIGHBOUR nodes, which get `penalty + local` instead of xi from the threads that own the local sequence
         auto issue_score = [&](int nt) {
-          const uint32_t eB = (nt & 1) ? bufB : bufA;
           const uint32_t d = tm + SC_S + (nt & 1) * 128;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma::mma_f16_ts(d, tm + SC_Q + 64 + 8 * ks, umma::make_desc(eB + ks * 2 * lboN, lboN, 128), idescS, ks > 0);
+            umma::mma_f16_ts(d, tm + SC_Q + 64 + 8 * ks, umma::make_desc(bufA + ks * 2 * lboN, lboN, 128), idescS, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma::mma_f16_ts(d, tm + SC_Q + 8 * ks, umma::make_desc(eB + 32768u + ks * 2 * lboN, lboN, 128), idescS, true);
+            umma::mma_f16_ts(d, tm + SC_Q + 8 * ks, umma::make_desc(bufA + 32768u + ks * 2 * lboN, lboN, 128), idescS, true);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma::mma_f16_ts(d, tm + SC_Q + 8 * ks, umma::make_desc(eB + ks * 2 * lboN, lboN, 128), idescS, true);
-          umma::commit(bar_scm + (nt & 1));
+            umma::mma_f16_ts(d, tm + SC_Q + 8 * ks, umma::make_desc(bufA + ks * 2 * lboN, lboN, 128), idescS, true);
+          umma::commit(bar_scm);
         };
-        if (tid == 0) {
-          umma::fence_after_sync();
-          mbar_wait(bar_e, ph_e[0]);
-          issue_score(0);
-        }
-        ph_e[0] ^= 1;
+        float* sSc = sm + L::buf + 16384;                 // scratch: score of node jl of this tile at [row][jl ^ (row & 31)]
         float xbest = -INFINITY, vbest = -INFINITY, win = 0.f;
         int ibest = 0x7fffffff;
         auto consider = [&](float x, int j) {
@@ -712,21 +705,22 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
             if (x > xbest) { xbest = x; win = fmaxf(1e-4f, 5e-7f * __expf(2.f * fabsf(x))); }
           }
         };
+        const int npr = act ? sNp[row] : 0;
         for (int nt = 0; nt < NT; ++nt) {
           const int sl2 = nt & 1;
-          if (tid == 0 && nt + 1 < NT) {
-            mbar_wait(bar_e + (sl2 ^ 1), ph_e[sl2 ^ 1]);
+          if (tid == 0) {
+            mbar_wait(bar_e, ph_e[0]);
             umma::fence_after_sync();
-            issue_score(nt + 1);
+            issue_score(nt);
           }
-          if (nt + 1 < NT) ph_e[sl2 ^ 1] ^= 1;
-          mbar_wait(bar_scm + sl2, ph_sc[sl2]);
-          ph_sc[sl2] ^= 1;
+          ph_e[0] ^= 1;
+          mbar_wait(bar_scm, ph_sc[0]);
+          ph_sc[0] ^= 1;
           umma::fence_after_sync();
-          if (tid == 0 && nt + 2 < NT) {        // this tile's E' buffer is free again
+          if (tid == 0 && nt + 1 < NT) {        // the E' buffer is free again: the next tile streams in while this one is read
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar_e + sl2, 65536u);
-            bulk_g2s(sm + L::buf + sl2 * 16384, et + (size_t)(nt + 2) * ELG_TILE_BYTES, 65536u, bar_e + sl2);
+            mbar_expect_tx(bar_e, 65536u);
+            bulk_g2s(sm + L::buf, et + (size_t)(nt + 1) * ELG_TILE_BYTES, 65536u, bar_e);
           }
           {
             uint32_t xr[32];
@@ -738,48 +732,41 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
               const uint32_t vwin = ~gmask[4 * nt + wsub] & (nb >= 32 ? FULL : (nb > 0 ? ((1u << nb) - 1u) : 0u));
               const uint32_t nwin = gnb[4 * nt + wsub];
               const float* ebt = sEb + sl2 * 128 + 32 * wsub;
+              float* scr = sSc + row * 128;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 if ((vwin >> i) & 1u) {
                   const float sc = umma::after_wait(xr[i]);
-                  if ((nwin >> i) & 1u) gsc[jb + i] = sc;                    // a neighbour: exact logit later
+                  if ((nwin >> i) & 1u) scr[(32 * wsub + i) ^ lane] = sc + ebt[i];      // a neighbour: exact logit below
                   else consider((sc + ebt[i]) + A.xi, jb + i);
                 }
               }
             }
           }
           umma::fence_before_sync();
-          __syncthreads();                       // S buffer and eb slot of this tile may be overwritten (tile nt + 2)
-          if (nt + 2 < NT) {
-            const int j = (nt + 2) * 128 + (tid & 127);
-            if (tid < 128) sEb[sl2 * 128 + tid] = j < N1 ? pEb[j] : 0.f;
-          }
-          if (nt + 2 < NT || nt + 1 < NT) __syncthreads();
-        }
-        PHASE_MARK(8);
-        // ---- the neighbours (and the depot) with their own penalty + local score -------------------------------------------
-        if (act) {
-          const int npr = sNp[row];
-          int ndv[SPT];
-          float xv[SPT];
+          __syncthreads();
+          // the neighbours of this tile (and the depot) with their own penalty + local score; only the depot can be masked
+          if (act) {
 #pragma unroll
-          for (int s = 0; s < SPT; ++s) {            // every load first (independent L2 round trips), then the comparisons
-            const int p = p0 + s;
-            ndv[s] = -1;
-            xv[s] = 0.f;
-            if (p < npr) {
-              const int nd = sAddId[row * SKT + p];
-              const bool masked = (gmask[nd >> 5] >> (nd & 31)) & 1u;
-              xv[s] = (gsc[nd] + pEb[nd]) + sAdd[row * SKT + p];
-              ndv[s] = masked ? -2 - nd : nd;
+            for (int s = 0; s < SPT; ++s) {
+              const int p = p0 + s;
+              if (p < npr) {
+                const int nd = sAddId[row * SKT + p];
+                if ((nd >> 7) == nt) {
+                  const bool masked = DEP && p == 0 && (gmask[0] & 1u);
+                  if (!masked) consider(scr_at(sSc, row, nd & 127, lane) + sAdd[row * SKT + p], nd);
+                  gnb[nd >> 5] = 0u;
+                }
+              }
             }
           }
-#pragma unroll
-          for (int s = 0; s < SPT; ++s) {
-            if (ndv[s] >= 0) consider(xv[s], ndv[s]);
-            if (ndv[s] != -1) gnb[(ndv[s] >= 0 ? ndv[s] : -2 - ndv[s]) >> 5] = 0u;
+          if (nt + 1 < NT) {
+            const int j = (nt + 1) * 128 + (tid & 127);
+            if (tid < 128) sEb[(sl2 ^ 1) * 128 + tid] = j < N1 ? pEb[j] : 0.f;
+            __syncthreads();                     // scratch and eb slot may be rewritten by the next tile
           }
         }
+        PHASE_MARK(8);
         sX2[wsub * 128 + row] = make_float2(vbest, __int_as_float(ibest));
         __syncthreads();
         {

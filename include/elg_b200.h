@@ -119,7 +119,7 @@ typedef struct elg_tables {
                              (elg_et_bytes() per batch); written by elg_encode when non-NULL; with it (and ws) greedy
                              rollouts of large instances run on the streamed tensor-core kernel (rollout_stc.cu)          */
   void* ws;               /* scratch of that kernel, elg_rollout_ws_bytes(): per-row bit masks (masked / visited /
-                             neighbour) and per-row scores of the neighbour nodes; contents need not be preserved        */
+                             neighbour), one word per 32 nodes; contents need not be preserved                           */
 } elg_tables;
 
 #define ELG_TILE_NODES 128                          /* nodes per operand tile of elg_tables.et        */

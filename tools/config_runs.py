@@ -92,6 +92,36 @@ def cvrp1000(n=4):
             "aug_cost": float(aug.mean()), "feasible": True}
 
 
+def cvrp_xxl(N=7000):
+    """A synthetic instance of CVRPLIB Set-XXL size (Antwerp2: 7000 customers) with the reference driver's POMO width
+    min(N, 1000): the largest shapes of the streamed kernel (220 mask words per row, neighbour lists of 55 chunks)."""
+    from elg_b200.cvrp import CVRPEnv, CVRPModel
+    from elg_b200.cvrp.test import solve_batch
+    mp = dict(DEFAULT_MODEL_PARAMS["cvrp"])
+    sd = synthetic_state_dict("cvrp", seed=1234, gain=3.0)
+    data = synthetic_cvrp_batch(1, N, seed=7)
+    data["demand"] = data["demand"] * (50.0 / 700.0)          # ~ Set-XXL capacities: about 140 customers per route
+    model = CVRPModel(**mp)
+    model.decoder.add_local_policy(DEV)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval().requires_grad_(False)
+    env = CVRPEnv(1000, DEV)
+    dev = {k: v.to(DEV) for k, v in data.items()}
+    random.seed(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    no_aug, aug, sol, rew = solve_batch(model, env, dev, 8)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    prob = O.load_cvrp(data["depot"], data["loc"], data["demand"], 8)
+    O.check_feasible_cvrp(sol[:1, :8].cpu(), prob.demand[:1])
+    return {"config": "synthetic CVRP%d (Set-XXL size), x8 aug, POMO width 1000, seeded random-init weights" % N, "seconds": secs,
+            "rollout_steps_T": int(sol.shape[2]), "ms_per_decode_step": 1e3 * secs / int(sol.shape[2]), "aug_cost": float(aug.mean()),
+            "feasible": True}
+
+
 if __name__ == "__main__":
     out = {"tsp100": tsp100(), "cvrp1000": cvrp1000()}
+    if "--xxl" in sys.argv:
+        out["cvrp_xxl"] = cvrp_xxl()
     print(json.dumps(out, indent=1))
