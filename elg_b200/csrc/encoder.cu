@@ -390,134 +390,255 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restric
 // fp32 in TMEM (two accumulators: hi*hi | cross terms; fp32-matmul-grade accuracy, tools/umma_precision_experiment.py)
 // -- plain TF32/BF16 inputs would break the 1e-4 logit tolerance.  One CTA = 128 rows; the fp32 activations are split on the fly into the K-major
 // core-matrix operand layout (umma.cuh), the weights were pre-split at model load (split_weights_kernel) and arrive
-// by TMA bulk copy, 32 KB per (n-tile, 64-wide k-block).  96 KB smem -> 2 CTAs/SM hide each other's TMA / MMA latency.
-constexpr int TG_SMEM = 65536 + 32768 + 64;
+// by TMA bulk copy from 32 KB (n-tile, 64-wide k-block) tiles.
+// Persistent and warp-specialised (round 2): one CTA per SM walks m-tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+//   warps 0-3   epilogue: drain an accumulator set (TMEM lane = row) 32 columns at a time through a swizzled 4 KB
+//               staging tile per warp, so every global store / residual load instruction covers four full 128-byte lines
+//   warps 4-11  builders: fp32 activation block (128 x 128) -> fp16 hi/lo operand tiles, double-buffered, so the block of
+//               the next m-tile (or k super-block) is converted while the tensor core works on the current one;
+//               lane = (row % 8, 8-wide k-chunk): 32-byte global sectors in, conflict-free 16-byte core-matrix rows out
+//   warp 12     MMA issuer: split-precision MMAs of a 32-wide k-block as soon as its B stage and the A block have landed;
+//               tcgen05.commit frees the stage / the A block; TWO accumulator sets (2 x 256 TMEM columns), so the
+//               epilogue of one n-tile overlaps the MMAs of the next
+//   warp 13     TMA producer: 16 KB weight stages (n-tile, 32-wide k-block: hi 8 KB + lo 8 KB) through a 5-stage ring
+// K = 128 with any number of n-tiles, or one n-tile with K a multiple of 128 (the encoder's shapes).
+constexpr int TG_A_BYTES = 65536, TG_B_BYTES = 16384, TG_STAGES = 5, TG_STAGE_TILE = 4096;
+constexpr int TG_OFF_B = 2 * TG_A_BYTES, TG_OFF_STG = TG_OFF_B + TG_STAGES * TG_B_BYTES, TG_OFF_BAR = TG_OFF_STG + 4 * TG_STAGE_TILE;
+constexpr int TG_SMEM = TG_OFF_BAR + 256;
+constexpr int TG_THREADS = 448;      // 4 epilogue + 8 builder warps + MMA issuer + TMA producer
+static_assert(TG_SMEM <= 232448, "tc_gemm_kernel shared memory");
 
 __device__ __forceinline__ void tg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tg_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   umma::smem_addr(dst)), "l"(src), "r"(bytes), "r"(umma::smem_addr(bar)) : "memory");
+__device__ __forceinline__ void tg_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_addr(bar)) : "memory");
 }
+__device__ __forceinline__ void tg_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(umma::smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tg_epi_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void tg_builders_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// cplane: element offset between the outputs of consecutive n-tiles (0 = n-tile nt writes columns [128 nt, 128 nt + 128)
+// of C; otherwise n-tile nt writes columns [0, 128) of the plane C + nt * cplane -- several N = 128 products of one input)
 template <int EPI>
-__global__ void __launch_bounds__(256, 2) tc_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Ws,
-                                                         float* __restrict__ C, const float* __restrict__ bias,
-                                                         const float* __restrict__ res, long long M, int N, int K, int ldc) {
+__global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Ws,
+                                                                float* __restrict__ C, const float* __restrict__ bias,
+                                                                const float* __restrict__ res, long long M, int N, int K, int ldc,
+                                                                long long cplane) {
   extern __shared__ __align__(1024) uint8_t tsm[];
-  uint8_t* aHi = tsm;                  // 128 rows x 128 k (one k super-block), fp16 hi
-  uint8_t* aLo = tsm + 32768;
-  uint8_t* bT = tsm + 65536;           // [hi 16 KB | lo 16 KB] weight tile: 128 rows (n) x 64 k
-  uint64_t* barB = reinterpret_cast<uint64_t*>(tsm + 98304);
-  uint64_t* barM = barB + 1;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(barB + 2);
+  uint8_t* aBuf = tsm;                                   // [2][hi 32 KB | lo 32 KB]: 128 rows x 128 k
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + TG_OFF_BAR);
+  uint64_t* b_full = bars;                      // [5] TMA landed
+  uint64_t* b_empty = bars + TG_STAGES;         // [5] MMAs of the stage done
+  uint64_t* a_full = bars + 2 * TG_STAGES;      // [2] builders wrote the A block
+  uint64_t* a_empty = a_full + 2;               // [2] MMAs of the A block done
+  uint64_t* acc_full = a_full + 4;              // [2] accumulator set complete
+  uint64_t* acc_empty = a_full + 6;             // [2] accumulator set drained
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(a_full + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long m0 = (long long)blockIdx.x * 128;
-  if (warp == 0) umma::tmem_alloc(tptr, 256);      // accumulator 0: hi*hi, accumulator 1 (cols 128..): cross terms
-  if (tid == 0) { umma::mbar_init(barB, 1); umma::mbar_init(barM, 1); }
+  if (warp == 0) umma::tmem_alloc(tptr, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * TG_STAGES + 8; ++i) umma::mbar_init(bars + i, 1);
+  }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tbase = *tptr;
   const int nT = N >> 7, kS = K >> 7;
-  const uint32_t idesc = umma::make_idesc_f16(128, 128);
-  uint32_t phB = 0, phM = 0;
-  for (int nt = 0; nt < nT; ++nt) {
-    for (int ks = 0; ks < kS; ++ks) {
-      if (nt == 0 || kS > 1) {           // (re)build the A operand of this 128-wide k super-block
-        for (int i = tid; i < 128 * 32; i += 256) {
-          const int r = i >> 5, k4 = (i & 31) * 4;
-          const long long row = m0 + r;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < M) v = *reinterpret_cast<const float4*>(A + row * K + ks * 128 + k4);
-          __half h0, l0, h1, l1, h2, l2, h3, l3;
-          umma::split_f16(v.x, h0, l0); umma::split_f16(v.y, h1, l1);
-          umma::split_f16(v.z, h2, l2); umma::split_f16(v.w, h3, l3);
-          const uint32_t off = umma::elem_off(r, k4, 2048);
-          *reinterpret_cast<uint2*>(aHi + off) = make_uint2((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16),
-                                                            (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16));
-          *reinterpret_cast<uint2*>(aLo + off) = make_uint2((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16),
-                                                            (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16));
+  const long long n_tiles = (M + 127) >> 7;
+
+  if (warp == 13) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      const uint32_t b0 = umma::smem_addr(tsm + TG_OFF_B);
+      uint32_t bi = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int nt = 0; nt < nT; ++nt)
+          for (int kb = 0; kb < (K >> 5); ++kb, ++bi) {
+            const uint32_t st = bi % TG_STAGES;
+            if (bi >= TG_STAGES) umma::mbar_wait(b_empty + st, ((bi / TG_STAGES) - 1) & 1);
+            const uint8_t* src = Ws + ((size_t)nt * (K >> 6) + (kb >> 1)) * 32768 + (kb & 1) * 8192;
+            tg_mbar_expect_tx(b_full + st, TG_B_BYTES);
+            tg_bulk_g2s(b0 + st * TG_B_BYTES, src, 8192, b_full + st);                   // hi: 128 n x 32 k
+            tg_bulk_g2s(b0 + st * TG_B_BYTES + 8192, src + 16384, 8192, b_full + st);    // lo
+          }
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_f16(128, 128);
+      const uint32_t a0 = umma::smem_addr(aBuf), b0 = umma::smem_addr(tsm + TG_OFF_B);
+      uint32_t bi = 0, ai = 0, ci = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ai += kS)
+        for (int nt = 0; nt < nT; ++nt, ++ci) {
+          const uint32_t acc = ci & 1;
+          if (ci >= 2) umma::mbar_wait(acc_empty + acc, ((ci >> 1) - 1) & 1);
+          umma::fence_after_sync();
+          const uint32_t d0 = tbase + acc * 256;
+          for (int ks = 0; ks < kS; ++ks) {
+            const uint32_t aidx = ai + ks, slot = aidx & 1;
+            if (nt == 0) umma::mbar_wait(a_full + slot, (aidx >> 1) & 1);
+            const uint32_t aHi = a0 + slot * TG_A_BYTES, aLo = aHi + 32768;
+            for (int kb = 0; kb < 4; ++kb, ++bi) {
+              const uint32_t st = bi % TG_STAGES;
+              umma::mbar_wait(b_full + st, (bi / TG_STAGES) & 1);
+              umma::fence_after_sync();
+              const uint32_t bHi = b0 + st * TG_B_BYTES, bLo = bHi + 8192;
+#pragma unroll
+              for (int term = 0; term < 3; ++term) {
+                const uint32_t a = (term == 2 ? aLo : aHi) + kb * 4 * 2048;
+                const uint32_t b2 = term == 1 ? bLo : bHi;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+                  // the small cross terms get their own accumulator: added into the large hi*hi sums, the tensor core's
+                  // internal alignment would truncate them (measured 4x error, tools/umma_precision_experiment.py)
+                  umma::mma_f16_ss(d0 + (term ? 128u : 0u), umma::make_desc(a + kk * 4096, 2048, 128),
+                                   umma::make_desc(b2 + kk * 4096, 2048, 128), idesc,
+                                   !(ks == 0 && kb == 0 && (term == 0 || term == 1) && kk == 0));
+              }
+              umma::commit(b_empty + st);
+            }
+            if (nt == nT - 1) umma::commit(a_empty + slot);
+          }
+          umma::commit(acc_full + acc);
+        }
+    }
+  } else if (warp >= 4) {
+    // ---------------- builders: A operand blocks ----------------
+    const int bw = warp - 4, r8 = lane & 7, cj = (bw & 3) * 4 + (lane >> 3), rh = bw >> 2;   // k in [8 cj, 8 cj + 8), rows [64 rh, 64 rh + 64)
+    uint32_t aidx = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long m0 = tile * 128;
+      for (int ks = 0; ks < kS; ++ks, ++aidx) {
+        const uint32_t slot = aidx & 1;
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {                 // the thread's 16 loads of the block in flight before the conversions
+          const long long row = m0 + (rh * 8 + it) * 8 + r8;
+          const float* src = A + row * K + ks * 128 + cj * 8;
+          if (row < M) {
+            v[2 * it] = *reinterpret_cast<const float4*>(src);
+            v[2 * it + 1] = *reinterpret_cast<const float4*>(src + 4);
+          } else {
+            v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (aidx >= 2) umma::mbar_wait(a_empty + slot, ((aidx >> 1) - 1) & 1);
+        uint8_t* aHi = aBuf + slot * TG_A_BYTES;
+        uint8_t* aLo = aHi + 32768;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          uint4 h, l;
+          umma::split2_f16(v[2 * it].x, v[2 * it].y, h.x, l.x);
+          umma::split2_f16(v[2 * it].z, v[2 * it].w, h.y, l.y);
+          umma::split2_f16(v[2 * it + 1].x, v[2 * it + 1].y, h.z, l.z);
+          umma::split2_f16(v[2 * it + 1].z, v[2 * it + 1].w, h.w, l.w);
+          const uint32_t off = (uint32_t)cj * 2048u + (uint32_t)(rh * 8 + it) * 128u + (uint32_t)r8 * 16u;
+          *reinterpret_cast<uint4*>(aHi + off) = h;
+          *reinterpret_cast<uint4*>(aLo + off) = l;
         }
         umma::fence_async_smem();
+        tg_builders_sync();
+        if (tid == 128) tg_mbar_arrive(a_full + slot);
       }
-      for (int half = 0; half < 2; ++half) {
-        __syncthreads();                 // A operand written; every thread is past the previous MMA wait (B tile free)
-        if (tid == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          tg_mbar_expect_tx(barB, 32768);
-          tg_bulk_g2s(bT, Ws + ((size_t)nt * (K >> 6) + ks * 2 + half) * 32768, 32768, barB);
-          umma::mbar_wait(barB, phB);
-          umma::fence_after_sync();
+    }
+  } else {
+    // ---------------- epilogue: TMEM lane = row; warp = lane quadrant = 32 rows ----------------
+    float* stg = reinterpret_cast<float*>(tsm + TG_OFF_STG + warp * TG_STAGE_TILE);     // [32 rows][8 float4], float4 index ^ (row & 7)
+    const int er = lane >> 3, ec = lane & 7;
+    // residual rows of the NEXT 32-column chunk are requested before the current chunk is drained (across n-tile and
+    // m-tile boundaries), so their DRAM latency hides behind the accumulator wait and the stores
+    float4 rr[8];
+    auto fetch_res = [&](long long tile, int nt, int c) {
+      const int nbase = cplane ? 0 : nt * 128;
 #pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t a = umma::smem_addr(term == 2 ? aLo : aHi) + half * 8 * 2048;
-            const uint32_t b = umma::smem_addr(bT) + (term == 1 ? 16384 : 0);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              // the small cross terms get their own accumulator: added into the large hi*hi sums, the tensor core's
-              // internal alignment would truncate them (measured 4x error, tools/umma_precision_experiment.py)
-              umma::mma_f16_ss(tbase + (term ? 128u : 0u), umma::make_desc(a + kk * 4096, 2048, 128),
-                               umma::make_desc(b + kk * 4096, 2048, 128), idesc,
-                               !(ks == 0 && half == 0 && (term == 0 || term == 1) && kk == 0));
-          }
-          umma::commit(barM);
-        }
-        phB ^= 1;
-        umma::mbar_wait(barM, phM);
-        phM ^= 1;
+      for (int k = 0; k < 8; ++k) {
+        const long long row = tile * 128 + 32 * warp + 4 * k + er;
+        rr[k] = (tile < n_tiles && row < M) ? *reinterpret_cast<const float4*>(res + (size_t)row * ldc + nbase + c * 32 + 4 * ec)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (EPI == EPI_BIAS_RES) fetch_res(blockIdx.x, 0, 0);
+    uint32_t ci = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long m0 = tile * 128 + 32 * warp;
+      for (int nt = 0; nt < nT; ++nt, ++ci) {
+        const uint32_t acc = ci & 1;
+        umma::mbar_wait(acc_full + acc, (ci >> 1) & 1);
         umma::fence_after_sync();
-      }
-    }
-    // epilogue: TMEM lane = row; warp quadrant = 32 rows, warp / 4 = 64-column half
-    {
-      const int q = warp & 3, ch = warp >> 2;
-      const long long row = m0 + 32 * q + lane;
+        float* Cp = cplane ? C + nt * cplane : C;
+        const int nbase = cplane ? 0 : nt * 128;
+        const uint32_t t0 = tbase + ((uint32_t)(32 * warp) << 16) + acc * 256;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES)
+            bb = *reinterpret_cast<const float4*>(bias + nt * 128 + c * 32 + 4 * ec);
+          uint32_t v[32], v2[32];
+          umma::ld32_nw(t0 + c * 32, v);
+          umma::ld32_nw(t0 + 128 + c * 32, v2);
+          umma::wait_ld();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col0 = ch * 64 + c * 16;
-        float v[16], v2[16];
-        umma::ld16(tbase + ((uint32_t)(32 * q) << 16) + col0, v);
-        umma::ld16(tbase + ((uint32_t)(32 * q) << 16) + 128 + col0, v2);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += v2[i];
-        if (row < M) {
-          const int n = nt * 128 + col0;
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            float4 o = make_float4(v[i4 * 4], v[i4 * 4 + 1], v[i4 * 4 + 2], v[i4 * 4 + 3]);
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + n + i4 * 4);
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (EPI == EPI_BIAS_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (EPI == EPI_BIAS_RES) {
-              const float4 rr = *reinterpret_cast<const float4*>(res + row * ldc + n + i4 * 4);
-              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-            }
-            *reinterpret_cast<float4*>(C + row * ldc + n + i4 * 4) = o;
+          for (int i4 = 0; i4 < 8; ++i4) {
+            float4 o;
+            o.x = umma::after_wait(v[4 * i4]) + umma::after_wait(v2[4 * i4]);
+            o.y = umma::after_wait(v[4 * i4 + 1]) + umma::after_wait(v2[4 * i4 + 1]);
+            o.z = umma::after_wait(v[4 * i4 + 2]) + umma::after_wait(v2[4 * i4 + 2]);
+            o.w = umma::after_wait(v[4 * i4 + 3]) + umma::after_wait(v2[4 * i4 + 3]);
+            *reinterpret_cast<float4*>(stg + lane * 32 + 4 * (i4 ^ (lane & 7))) = o;
           }
+          __syncwarp();
+          float4 o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = 4 * k + er;
+            o[k] = *reinterpret_cast<const float4*>(stg + r * 32 + 4 * (ec ^ (r & 7)));
+            o[k].x += bb.x; o[k].y += bb.y; o[k].z += bb.z; o[k].w += bb.w;
+            if (EPI == EPI_BIAS_RELU) { o[k].x = fmaxf(o[k].x, 0.f); o[k].y = fmaxf(o[k].y, 0.f); o[k].z = fmaxf(o[k].z, 0.f); o[k].w = fmaxf(o[k].w, 0.f); }
+            if (EPI == EPI_BIAS_RES) { o[k].x += rr[k].x; o[k].y += rr[k].y; o[k].z += rr[k].z; o[k].w += rr[k].w; }
+          }
+          if (EPI == EPI_BIAS_RES) {       // next chunk in (tile, nt, c) order
+            const bool last_c = c == 3, last_nt = nt == nT - 1;
+            fetch_res(last_c && last_nt ? tile + gridDim.x : tile, last_c ? (last_nt ? 0 : nt + 1) : nt, last_c ? 0 : c + 1);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const long long row = m0 + 4 * k + er;
+            if (row < M) *reinterpret_cast<float4*>(Cp + (size_t)row * ldc + nbase + c * 32 + 4 * ec) = o[k];
+          }
+          __syncwarp();
         }
+        umma::fence_before_sync();
+        tg_epi_sync();
+        if (tid == 0) tg_mbar_arrive(acc_empty + acc);
       }
     }
-    umma::fence_before_sync();
-    __syncthreads();                     // accumulator reads done before the next n-tile overwrites TMEM
   }
-  if (warp == 0) umma::tmem_dealloc(tbase, 256);
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
 template <int EPI>
 static int tc_gemm(const float* A, const float* derived, long long split_off, float* C, const float* bias, const float* res,
-                   long long M, int N, int K, int ldc, cudaStream_t st) {
+                   long long M, int N, int K, int ldc, cudaStream_t st, long long cplane = 0) {
   ELG_REQUIRE(N % 128 == 0 && K % 128 == 0, ELG_EUNSUPPORTED, "tc_gemm needs N%%128==0 and K%%128==0 (N=%d K=%d)", N, K);
+  ELG_REQUIRE(N == 128 || K == 128, ELG_EUNSUPPORTED, "tc_gemm: K = 128 or a single n-tile (N=%d K=%d)", N, K);
   static bool attr = false;
+  static int sms = 0;
   if (!attr) {
     ELG_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+    int dev = 0;
+    ELG_CUDA_OK(cudaGetDevice(&dev));
+    ELG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr = true;
   }
-  tc_gemm_kernel<EPI><<<(unsigned)((M + 127) / 128), 256, TG_SMEM, st>>>(A, reinterpret_cast<const uint8_t*>(derived + split_off), C,
-                                                                        bias, res, M, N, K, ldc);
+  const long long tiles = (M + 127) / 128;
+  tc_gemm_kernel<EPI><<<(unsigned)(tiles < sms ? tiles : sms), TG_THREADS, TG_SMEM, st>>>(
+      A, reinterpret_cast<const uint8_t*>(derived + split_off), C, bias, res, M, N, K, ldc, cplane);
   ELG_LAUNCH_OK();
   return ELG_OK;
 }
@@ -724,8 +845,17 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
   // decoder-side tables from the encoded nodes
   const float* enc = t->enc;
   const long long sd = split_off_dec(d->layers, d->ff);
-  ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd, t->k, nullptr, nullptr, rows, E, E, E, st));
-  ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 1LL * E * E, t->v, nullptr, nullptr, rows, E, E, E, st));
+  // decoder tables K', V, qtab (and qfirst, tsp) are products of the same input with four consecutive pre-split weight
+  // matrices: one launch with n-tile i written to plane i when the caller's buffers are equally spaced (the engine's are)
+  const int n_dec = d->problem == ELG_TSP ? 4 : 3;
+  const long long plane = t->v - t->k;
+  const bool fused_dec = plane >= (long long)rows * E && t->qtab - t->v == plane && (n_dec == 3 || t->qfirst - t->qtab == plane);
+  if (fused_dec) {
+    ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd, t->k, nullptr, nullptr, rows, n_dec * E, E, E, st, plane));
+  } else {
+    ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd, t->k, nullptr, nullptr, rows, E, E, E, st));
+    ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 1LL * E * E, t->v, nullptr, nullptr, rows, E, E, E, st));
+  }
   if (rollout_is_resident(d, N1)) {
     ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(d, B, N1), st));      // padded rows of the MMA operand must be zero
     ELG_TRY(gemm<EPI_UMMA_SPLIT>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
@@ -739,9 +869,11 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
       ELG_LAUNCH_OK();
     }
   }
-  ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 2LL * E * E, t->qtab, nullptr, nullptr, rows, E, E, E, st));
-  if (d->problem == ELG_TSP)
-    ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 3LL * E * E, t->qfirst, nullptr, nullptr, rows, E, E, E, st));
+  if (!fused_dec) {
+    ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 2LL * E * E, t->qtab, nullptr, nullptr, rows, E, E, E, st));
+    if (d->problem == ELG_TSP)
+      ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 3LL * E * E, t->qfirst, nullptr, nullptr, rows, E, E, E, st));
+  }
   row_dot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(enc, derived + DER_BE, rows, t->eb);
   ELG_LAUNCH_OK();
   if (t->nbr) ELG_TRY(launch_neighbours(d, t->xy, t->demand, B, N1, t->nbr, st));

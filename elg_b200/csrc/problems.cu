@@ -78,17 +78,23 @@ __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, cons
   // the same values once more in list (rank) order, with the node's demand and id: one 16-byte record per list entry
   // (rollout_tc.cu reads the records of the chosen ranks instead of chasing list byte -> pair table -> demand)
   float4* rec = reinterpret_cast<float4*>(row + ELG_NBR_STRIDE + ELG_NBR_PAIR_BYTES(N1));
-  for (int j = threadIdx.x; j < N1; j += blockDim.x) feat[j] = make_float2(sd[j], atan2f(p[2 * j + 1] - yi, p[2 * j] - xi));
+  // resident instances have N1 <= 112 <= blockDim.x: thread j owns node j (distance, angle computed once, used twice)
+  const int j = threadIdx.x;
+  float thj = 0.f;
+  if (j < N1) {
+    thj = atan2f(p[2 * j + 1] - yi, p[2 * j] - xi);
+    feat[j] = make_float2(sd[j], thj);
+  }
   __syncthreads();
-  for (int j = j0 + threadIdx.x; j < N1; j += blockDim.x) {
-    float dj = sd[j];
+  if (j >= j0 && j < N1) {
+    const float dj = sd[j];
     int rank = 0;
     for (int k = j0; k < N1; ++k) {
-      float dk = sd[k];
+      const float dk = sd[k];
       rank += (dk < dj) || (dk == dj && k < j);
     }
     row[nbr_pos(rank)] = (uint8_t)j;
-    rec[rank] = make_float4(dj, atan2f(p[2 * j + 1] - yi, p[2 * j] - xi), demand ? demand[(size_t)b * N1 + j] : 0.f, __int_as_float(j));
+    rec[rank] = make_float4(dj, thj, demand ? demand[(size_t)b * N1 + j] : 0.f, __int_as_float(j));
   }
   for (int e = N1 - j0 + threadIdx.x; e < N1; e += blockDim.x) rec[e] = make_float4(0.f, 0.f, 0.f, 0.f);
 }

@@ -59,8 +59,9 @@ def generate_tsp_data(batch_size, problem_size, distribution, device="cuda:0", s
 
 
 # ---------------------------------------------------------------------------------------------- datasets
-# The reference's Dataset classes (CVRP/generate_data.py:108-171, TSP/generate_data.py:74-99): same constructor,
-# same items; files are read on the host, generated data comes from the device generators above.
+# Drop-ins for the reference's dataset helpers (CVRP/generate_data.py:91-171, TSP/generate_data.py:59-99): the same
+# names, constructor arguments, pickle format ([depot, loc, demand, capacity(, types, types, grid)] rows for cvrp,
+# coordinate lists for tsp) and items; implemented over one tensor-backed base class.
 import os
 import pickle
 
@@ -68,40 +69,40 @@ from torch.utils.data import Dataset
 
 
 def check_extension(filename):
-    return filename if os.path.splitext(filename)[1] == ".pkl" else filename + ".pkl"
+    """`name` -> `name.pkl` unless it already ends in .pkl"""
+    root, ext = os.path.splitext(filename)
+    return filename if ext == ".pkl" else filename + ".pkl"
 
 
 def save_dataset(dataset, filename):
-    filedir = os.path.split(filename)[0]
-    if filedir and not os.path.isdir(filedir):
-        os.makedirs(filedir)
-    with open(check_extension(filename), 'wb') as f:
-        pickle.dump(dataset, f, pickle.HIGHEST_PROTOCOL)
+    """Pickle `dataset` (highest protocol) to check_extension(filename), creating the directory."""
+    target = check_extension(filename)
+    os.makedirs(os.path.dirname(target) or ".", exist_ok=True)
+    with open(target, "wb") as fh:
+        pickle.dump(dataset, fh, pickle.HIGHEST_PROTOCOL)
 
 
 def make_instance(args):
-    depot, loc, demand, capacity, *args = args
-    grid_size = 1
-    if len(args) > 0:
-        depot_types, customer_types, grid_size = args
-    return {'loc': torch.tensor(loc, dtype=torch.float) / grid_size,
-            'demand': torch.tensor(demand, dtype=torch.float) / capacity,
-            'depot': torch.tensor(depot, dtype=torch.float) / grid_size}
+    """One pickled cvrp row -> {'loc', 'demand', 'depot'} float tensors: demands over capacity, coordinates over the grid size."""
+    depot, loc, demand, capacity = args[:4]
+    grid = args[6] if len(args) > 4 else 1
+    as_f = lambda v: torch.as_tensor(v, dtype=torch.float)
+    return {"loc": as_f(loc) / grid, "demand": as_f(demand) / capacity, "depot": as_f(depot) / grid}
 
 
-class VRPDataset(Dataset):
-    def __init__(self, filename=None, size=100, num_samples=10000, offset=0, distribution=None, device="cuda:0", seed=None):
-        super(VRPDataset, self).__init__()
+class _ListDataset(Dataset):
+    """Instances from a reference .pkl file (rows [offset, offset + num_samples)) or from the device generators."""
+
+    def __init__(self, filename, size, num_samples, offset, distribution, device, seed):
+        super().__init__()
         if filename is not None:
-            assert os.path.splitext(filename)[1] == '.pkl'
-            with open(filename, 'rb') as f:
-                data = pickle.load(f)
-            self.data = [make_instance(args) for args in data[offset:offset + num_samples]]
+            if os.path.splitext(filename)[1] != ".pkl":
+                raise AssertionError("dataset files are .pkl")
+            with open(filename, "rb") as fh:
+                rows = pickle.load(fh)[offset:offset + num_samples]
+            self.data = [self._from_row(r) for r in rows]
         else:
-            dist = distribution if distribution is not None else {"data_type": "uniform"}
-            data = generate_vrp_data(num_samples, size, dist, device, seed)
-            self.data = [make_instance([data['depot'][i, 0].cpu().numpy(), data['loc'][i].cpu().numpy(),
-                                        data['demand'][i].cpu().numpy(), 1.0]) for i in range(num_samples)]
+            self.data = self._generate(num_samples, size, distribution or {"data_type": "uniform"}, device, seed)
         self.size = len(self.data)
 
     def __len__(self):
@@ -111,22 +112,26 @@ class VRPDataset(Dataset):
         return self.data[idx]
 
 
-class TSPDataset(Dataset):
+class VRPDataset(_ListDataset):
     def __init__(self, filename=None, size=100, num_samples=10000, offset=0, distribution=None, device="cuda:0", seed=None):
-        super(TSPDataset, self).__init__()
-        if filename is not None:
-            assert os.path.splitext(filename)[1] == '.pkl'
-            with open(filename, 'rb') as f:
-                data = pickle.load(f)
-            self.data = [torch.FloatTensor(row) for row in data[offset:offset + num_samples]]
-        else:
-            dist = distribution if distribution is not None else {"data_type": "uniform"}
-            data = generate_tsp_data(num_samples, size, dist, device, seed).cpu()
-            self.data = [data[i] for i in range(num_samples)]
-        self.size = len(self.data)
+        super().__init__(filename, size, num_samples, offset, distribution, device, seed)
 
-    def __len__(self):
-        return self.size
+    _from_row = staticmethod(make_instance)
 
-    def __getitem__(self, idx):
-        return self.data[idx]
+    @staticmethod
+    def _generate(n, size, dist, device, seed):
+        d = {k: v.cpu() for k, v in generate_vrp_data(n, size, dist, device, seed).items()}
+        return [{"loc": d["loc"][i], "demand": d["demand"][i], "depot": d["depot"][i, 0]} for i in range(n)]
+
+
+class TSPDataset(_ListDataset):
+    def __init__(self, filename=None, size=100, num_samples=10000, offset=0, distribution=None, device="cuda:0", seed=None):
+        super().__init__(filename, size, num_samples, offset, distribution, device, seed)
+
+    @staticmethod
+    def _from_row(row):
+        return torch.as_tensor(row, dtype=torch.float)
+
+    @staticmethod
+    def _generate(n, size, dist, device, seed):
+        return list(generate_tsp_data(n, size, dist, device, seed).cpu())
