@@ -392,20 +392,21 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restric
 // core-matrix operand layout (umma.cuh), the weights were pre-split at model load (split_weights_kernel) and arrive
 // by TMA bulk copy from 32 KB (n-tile, 64-wide k-block) tiles.
 // Persistent and warp-specialised (round 2): one CTA per SM walks m-tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-//   warps 0-3   epilogue: drain an accumulator set (TMEM lane = row) 32 columns at a time through a swizzled 4 KB
-//               staging tile per warp, so every global store / residual load instruction covers four full 128-byte lines
-//   warps 4-11  builders: fp32 activation block (128 x 128) -> fp16 hi/lo operand tiles, double-buffered, so the block of
+//   warps 0-7   epilogue: drain an accumulator set (TMEM lane = row; warp = (lane quadrant, 64-column half)) 16 columns at a
+//               time through a swizzled 2 KB staging tile per warp, so every global store / residual load instruction covers
+//               64 contiguous bytes of 8 rows (full sectors); residual rows are prefetched two chunks ahead
+//   warps 8-15  builders: fp32 activation block (128 x 128) -> fp16 hi/lo operand tiles, double-buffered, so the block of
 //               the next m-tile (or k super-block) is converted while the tensor core works on the current one;
 //               lane = (row % 8, 8-wide k-chunk): 32-byte global sectors in, conflict-free 16-byte core-matrix rows out
-//   warp 12     MMA issuer: split-precision MMAs of a 32-wide k-block as soon as its B stage and the A block have landed;
+//   warp 16     MMA issuer: split-precision MMAs of a 32-wide k-block as soon as its B stage and the A block have landed;
 //               tcgen05.commit frees the stage / the A block; TWO accumulator sets (2 x 256 TMEM columns), so the
 //               epilogue of one n-tile overlaps the MMAs of the next
-//   warp 13     TMA producer: 16 KB weight stages (n-tile, 32-wide k-block: hi 8 KB + lo 8 KB) through a 5-stage ring
+//   warp 17     TMA producer: 16 KB weight stages (n-tile, 32-wide k-block: hi 8 KB + lo 8 KB) through a 5-stage ring
 // K = 128 with any number of n-tiles, or one n-tile with K a multiple of 128 (the encoder's shapes).
-constexpr int TG_A_BYTES = 65536, TG_B_BYTES = 16384, TG_STAGES = 5, TG_STAGE_TILE = 4096;
-constexpr int TG_OFF_B = 2 * TG_A_BYTES, TG_OFF_STG = TG_OFF_B + TG_STAGES * TG_B_BYTES, TG_OFF_BAR = TG_OFF_STG + 4 * TG_STAGE_TILE;
+constexpr int TG_A_BYTES = 65536, TG_B_BYTES = 16384, TG_STAGES = 5, TG_STAGE_TILE = 2048;
+constexpr int TG_OFF_B = 2 * TG_A_BYTES, TG_OFF_STG = TG_OFF_B + TG_STAGES * TG_B_BYTES, TG_OFF_BAR = TG_OFF_STG + 8 * TG_STAGE_TILE;
 constexpr int TG_SMEM = TG_OFF_BAR + 256;
-constexpr int TG_THREADS = 448;      // 4 epilogue + 8 builder warps + MMA issuer + TMA producer
+constexpr int TG_THREADS = 576;      // 8 epilogue + 8 builder warps + MMA issuer + TMA producer
 static_assert(TG_SMEM <= 232448, "tc_gemm_kernel shared memory");
 
 __device__ __forceinline__ void tg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -418,7 +419,10 @@ __device__ __forceinline__ void tg_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(umma::smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void tg_epi_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void tg_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tg_epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 __device__ __forceinline__ void tg_builders_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // cplane: element offset between the outputs of consecutive n-tiles (0 = n-tile nt writes columns [128 nt, 128 nt + 128)
@@ -450,12 +454,28 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_kernel(const float* __r
   const int nT = N >> 7, kS = K >> 7;
   const long long n_tiles = (M + 127) >> 7;
 
-  if (warp == 13) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      const uint32_t b0 = umma::smem_addr(tsm + TG_OFF_B);
-      uint32_t bi = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  if (warp == 17) {
+    // ---------------- TMA producer (+ L2 prefetch of the activation / residual rows of the tiles ahead) ----------------
+    const uint32_t b0 = umma::smem_addr(tsm + TG_OFF_B);
+    const int ahead = 0;          // L2 bulk prefetch of the tiles ahead: measured slower (FFN2 707 -> 899 us), kept switched off
+    auto prefetch_tile = [&](long long tile) {
+      if (tile >= n_tiles) return;
+      const long long row0 = tile * 128;
+      const long long nrows = M - row0 < 128 ? M - row0 : 128;
+      if (kS == 1) {            // rows of 512 bytes: the whole block is contiguous
+        if (lane == 0) tg_prefetch_l2(A + row0 * K, (uint32_t)(nrows * 512));
+      } else {
+        for (long long r = lane; r < nrows; r += 32) tg_prefetch_l2(A + (row0 + r) * K, (uint32_t)(K * 4));
+      }
+      if (EPI == EPI_BIAS_RES && lane == 1) {
+        if (ldc == 128) tg_prefetch_l2(res + row0 * 128, (uint32_t)(nrows * 512));
+      }
+    };
+    uint32_t bi = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (ahead) prefetch_tile(tile + (long long)ahead * gridDim.x);
+      __syncwarp();
+      if (lane == 0) {
         for (int nt = 0; nt < nT; ++nt)
           for (int kb = 0; kb < (K >> 5); ++kb, ++bi) {
             const uint32_t st = bi % TG_STAGES;
@@ -465,8 +485,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_kernel(const float* __r
             tg_bulk_g2s(b0 + st * TG_B_BYTES, src, 8192, b_full + st);                   // hi: 128 n x 32 k
             tg_bulk_g2s(b0 + st * TG_B_BYTES + 8192, src + 16384, 8192, b_full + st);    // lo
           }
+      }
+      __syncwarp();
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = umma::make_idesc_f16(128, 128);
@@ -506,26 +528,31 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_kernel(const float* __r
           umma::commit(acc_full + acc);
         }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 8) {
     // ---------------- builders: A operand blocks ----------------
-    const int bw = warp - 4, r8 = lane & 7, cj = (bw & 3) * 4 + (lane >> 3), rh = bw >> 2;   // k in [8 cj, 8 cj + 8), rows [64 rh, 64 rh + 64)
+    const int bw = warp - 8, r8 = lane & 7, cj = (bw & 3) * 4 + (lane >> 3), rh = bw >> 2;   // k in [8 cj, 8 cj + 8), rows [64 rh, 64 rh + 64)
+    // rolling prefetch: the registers of a converted row group are refilled at once with the same group of the NEXT block
+    // (next k super-block or next m-tile), so loads stay in flight through the store / barrier / a_empty wait
+    float4 v[16];
+    auto fetch = [&](long long tile, int ks, int it) {
+      const long long row = tile * 128 + (rh * 8 + it) * 8 + r8;
+      const float* src = A + row * K + ks * 128 + cj * 8;
+      if (tile < n_tiles && row < M) {
+        v[2 * it] = *reinterpret_cast<const float4*>(src);
+        v[2 * it + 1] = *reinterpret_cast<const float4*>(src + 4);
+      } else {
+        v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int it = 0; it < 8; ++it) fetch(blockIdx.x, 0, it);
     uint32_t aidx = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long m0 = tile * 128;
       for (int ks = 0; ks < kS; ++ks, ++aidx) {
         const uint32_t slot = aidx & 1;
-        float4 v[16];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {                 // the thread's 16 loads of the block in flight before the conversions
-          const long long row = m0 + (rh * 8 + it) * 8 + r8;
-          const float* src = A + row * K + ks * 128 + cj * 8;
-          if (row < M) {
-            v[2 * it] = *reinterpret_cast<const float4*>(src);
-            v[2 * it + 1] = *reinterpret_cast<const float4*>(src + 4);
-          } else {
-            v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+        const bool last_ks = ks == kS - 1;
+        const long long ntile = last_ks ? tile + gridDim.x : tile;
+        const int nks = last_ks ? 0 : ks + 1;
         if (aidx >= 2) umma::mbar_wait(a_empty + slot, ((aidx >> 1) - 1) & 1);
         uint8_t* aHi = aBuf + slot * TG_A_BYTES;
         uint8_t* aLo = aHi + 32768;
@@ -536,78 +563,83 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_kernel(const float* __r
           umma::split2_f16(v[2 * it].z, v[2 * it].w, h.y, l.y);
           umma::split2_f16(v[2 * it + 1].x, v[2 * it + 1].y, h.z, l.z);
           umma::split2_f16(v[2 * it + 1].z, v[2 * it + 1].w, h.w, l.w);
+          fetch(ntile, nks, it);
           const uint32_t off = (uint32_t)cj * 2048u + (uint32_t)(rh * 8 + it) * 128u + (uint32_t)r8 * 16u;
           *reinterpret_cast<uint4*>(aHi + off) = h;
           *reinterpret_cast<uint4*>(aLo + off) = l;
         }
         umma::fence_async_smem();
         tg_builders_sync();
-        if (tid == 128) tg_mbar_arrive(a_full + slot);
+        if (tid == 256) tg_mbar_arrive(a_full + slot);
       }
     }
   } else {
-    // ---------------- epilogue: TMEM lane = row; warp = lane quadrant = 32 rows ----------------
-    float* stg = reinterpret_cast<float*>(tsm + TG_OFF_STG + warp * TG_STAGE_TILE);     // [32 rows][8 float4], float4 index ^ (row & 7)
-    const int er = lane >> 3, ec = lane & 7;
-    // residual rows of the NEXT 32-column chunk are requested before the current chunk is drained (across n-tile and
-    // m-tile boundaries), so their DRAM latency hides behind the accumulator wait and the stores
-    float4 rr[8];
-    auto fetch_res = [&](long long tile, int nt, int c) {
-      const int nbase = cplane ? 0 : nt * 128;
+    // ---------------- epilogue: TMEM lane = row; warp % 4 = lane quadrant (32 rows), warp / 4 = 64-column half ----------------
+    const int q = warp & 3, ch = warp >> 2;
+    float* stg = reinterpret_cast<float*>(tsm + TG_OFF_STG + warp * TG_STAGE_TILE);     // [32 rows][4 float4], float4 index ^ ((row >> 1) & 3)
+    const int er = lane >> 2, ec = lane & 3;                                             // store side: rows 8 k + er, float4 ec
+    // residual rows are requested TWO 16-column chunks ahead (across n-tile and m-tile boundaries), so their latency
+    // hides behind the accumulator wait and the stores of the chunks in between
+    float4 rr[2][4];
+    auto fetch_res = [&](float4* dst, long long tile, int nt, int c) {
+      const int col = (cplane ? 0 : nt * 128) + ch * 64 + c * 16 + 4 * ec;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const long long row = tile * 128 + 32 * warp + 4 * k + er;
-        rr[k] = (tile < n_tiles && row < M) ? *reinterpret_cast<const float4*>(res + (size_t)row * ldc + nbase + c * 32 + 4 * ec)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 4; ++k) {
+        const long long row = tile * 128 + 32 * q + 8 * k + er;
+        dst[k] = (tile < n_tiles && row < M) ? *reinterpret_cast<const float4*>(res + (size_t)row * ldc + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (EPI == EPI_BIAS_RES) fetch_res(blockIdx.x, 0, 0);
+    if (EPI == EPI_BIAS_RES) {
+      fetch_res(rr[0], blockIdx.x, 0, 0);
+      fetch_res(rr[1], blockIdx.x, 0, 1);
+    }
     uint32_t ci = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long m0 = tile * 128 + 32 * warp;
+      const long long m0 = tile * 128 + 32 * q;
       for (int nt = 0; nt < nT; ++nt, ++ci) {
         const uint32_t acc = ci & 1;
         umma::mbar_wait(acc_full + acc, (ci >> 1) & 1);
         umma::fence_after_sync();
         float* Cp = cplane ? C + nt * cplane : C;
-        const int nbase = cplane ? 0 : nt * 128;
-        const uint32_t t0 = tbase + ((uint32_t)(32 * warp) << 16) + acc * 256;
-#pragma unroll 1
+        const int nbase = (cplane ? 0 : nt * 128) + ch * 64;
+        const uint32_t t0 = tbase + ((uint32_t)(32 * q) << 16) + acc * 256 + ch * 64;
+        const bool last_nt = nt == nT - 1;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
           if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RES)
-            bb = *reinterpret_cast<const float4*>(bias + nt * 128 + c * 32 + 4 * ec);
-          uint32_t v[32], v2[32];
-          umma::ld32_nw(t0 + c * 32, v);
-          umma::ld32_nw(t0 + 128 + c * 32, v2);
+            bb = *reinterpret_cast<const float4*>(bias + nt * 128 + ch * 64 + c * 16 + 4 * ec);
+          uint32_t v[16], v2[16];
+          umma::ld16_nw(t0 + c * 16, v);
+          umma::ld16_nw(t0 + 128 + c * 16, v2);
           umma::wait_ld();
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
+          for (int i4 = 0; i4 < 4; ++i4) {
             float4 o;
             o.x = umma::after_wait(v[4 * i4]) + umma::after_wait(v2[4 * i4]);
             o.y = umma::after_wait(v[4 * i4 + 1]) + umma::after_wait(v2[4 * i4 + 1]);
             o.z = umma::after_wait(v[4 * i4 + 2]) + umma::after_wait(v2[4 * i4 + 2]);
             o.w = umma::after_wait(v[4 * i4 + 3]) + umma::after_wait(v2[4 * i4 + 3]);
-            *reinterpret_cast<float4*>(stg + lane * 32 + 4 * (i4 ^ (lane & 7))) = o;
+            *reinterpret_cast<float4*>(stg + lane * 16 + 4 * (i4 ^ ((lane >> 1) & 3))) = o;
           }
           __syncwarp();
-          float4 o[8];
+          float4 o[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int r = 4 * k + er;
-            o[k] = *reinterpret_cast<const float4*>(stg + r * 32 + 4 * (ec ^ (r & 7)));
+          for (int k = 0; k < 4; ++k) {
+            const int r = 8 * k + er;
+            o[k] = *reinterpret_cast<const float4*>(stg + r * 16 + 4 * (ec ^ ((r >> 1) & 3)));
             o[k].x += bb.x; o[k].y += bb.y; o[k].z += bb.z; o[k].w += bb.w;
             if (EPI == EPI_BIAS_RELU) { o[k].x = fmaxf(o[k].x, 0.f); o[k].y = fmaxf(o[k].y, 0.f); o[k].z = fmaxf(o[k].z, 0.f); o[k].w = fmaxf(o[k].w, 0.f); }
-            if (EPI == EPI_BIAS_RES) { o[k].x += rr[k].x; o[k].y += rr[k].y; o[k].z += rr[k].z; o[k].w += rr[k].w; }
+            if (EPI == EPI_BIAS_RES) { o[k].x += rr[c & 1][k].x; o[k].y += rr[c & 1][k].y; o[k].z += rr[c & 1][k].z; o[k].w += rr[c & 1][k].w; }
           }
-          if (EPI == EPI_BIAS_RES) {       // next chunk in (tile, nt, c) order
-            const bool last_c = c == 3, last_nt = nt == nT - 1;
-            fetch_res(last_c && last_nt ? tile + gridDim.x : tile, last_c ? (last_nt ? 0 : nt + 1) : nt, last_c ? 0 : c + 1);
+          if (EPI == EPI_BIAS_RES) {       // chunk c + 2 in (tile, nt, c) order
+            if (c < 2) fetch_res(rr[c & 1], tile, nt, c + 2);
+            else fetch_res(rr[c & 1], last_nt ? tile + gridDim.x : tile, last_nt ? 0 : nt + 1, c - 2);
           }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const long long row = m0 + 4 * k + er;
-            if (row < M) *reinterpret_cast<float4*>(Cp + (size_t)row * ldc + nbase + c * 32 + 4 * ec) = o[k];
+          for (int k = 0; k < 4; ++k) {
+            const long long row = m0 + 8 * k + er;
+            if (row < M) *reinterpret_cast<float4*>(Cp + (size_t)row * ldc + nbase + c * 16 + 4 * ec) = o[k];
           }
           __syncwarp();
         }
