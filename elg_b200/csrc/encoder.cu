@@ -675,6 +675,311 @@ static int tc_gemm(const float* A, const float* derived, long long split_off, fl
   return ELG_OK;
 }
 
+// ---- fused feed-forward block on tcgen05:  out = relu(x1 W1^T + b1) W2^T + b2 + x1  (CVRP/models.py:249-269) ----------
+// The hidden activations (rows x ff) never leave the SM: per 128-row tile and per 128-wide hidden chunk j
+//   M1(j)  acc1[j & 1] = x1 W1_j^T            SS MMAs, A = x1 operand (shared memory), B = W1 n-tile j (TMA ring)
+//   E(j)   epilogue warps: accumulator row -> + b1, ReLU -> fp16 hi/lo -> written IN PLACE over the accumulator columns
+//          as the tensor-memory A operand of the second contraction (lane = row; the rollout kernels' P operand again)
+//   M2(j)  acc2 += hid_j W2[:, chunk j]^T     TS MMAs, A in tensor memory, B = W2 k-blocks of chunk j (TMA ring)
+// issued as M1(0) M1(1) M2(0) M1(2) M2(1) M1(3) M2(2) M2(3): the tensor pipe works on the next chunk while the epilogue
+// warps convert the current one.  M1 keeps ONE accumulator and issues its cross terms first (lo stages before hi stages;
+// same accuracy as two accumulators, tools/umma_precision_experiment.py); acc2 collects four chunks and keeps the
+// cross terms in their own accumulator.  TMEM: [0,128) [128,256) acc1 / hid sets, [256,384) acc2, [384,512) acc2 cross.
+// Weight stages are the 16 KB hi or lo halves of the pre-split 32 KB (n-tile, 64-wide k-block) tiles.
+// Warps 0-3 epilogue, 4-7 builders (x1 block of the next tile), 8 MMA issuer, 9 TMA producer; persistent over m-tiles.
+constexpr int TF_STAGES = 5, TF_THREADS = 320;
+constexpr int TF_OFF_B = 2 * TG_A_BYTES, TF_OFF_STG = TF_OFF_B + TF_STAGES * 16384, TF_OFF_B1 = TF_OFF_STG + 4 * 4096;
+constexpr int TF_MAX_FF = 512;
+constexpr int TF_OFF_BAR = TF_OFF_B1 + TF_MAX_FF * 4, TF_SMEM = TF_OFF_BAR + 256;
+static_assert(TF_SMEM <= 232448, "tc_ffn_kernel shared memory");
+__device__ __forceinline__ void tf_group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(TF_THREADS, 1) tc_ffn_kernel(const float* __restrict__ X, const uint8_t* __restrict__ W1s,
+                                                               const float* __restrict__ b1, const uint8_t* __restrict__ W2s,
+                                                               const float* __restrict__ b2, float* __restrict__ out,
+                                                               float* __restrict__ hid_out, long long M, int FF) {
+  extern __shared__ __align__(1024) uint8_t tsm[];
+  uint8_t* aBuf = tsm;                                   // [2][hi 32 KB | lo 32 KB]: 128 rows x 128 k of x1
+  float* sB1 = reinterpret_cast<float*>(tsm + TF_OFF_B1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + TF_OFF_BAR);
+  uint64_t* b_full = bars;                      // [TF_STAGES]
+  uint64_t* b_empty = bars + TF_STAGES;         // [TF_STAGES]
+  uint64_t* a_full = bars + 2 * TF_STAGES;      // [2] builders wrote the x1 block
+  uint64_t* a_empty = a_full + 2;               // [2] first-contraction MMAs of the tile done
+  uint64_t* acc1_full = a_full + 4;             // [2] M1 of the chunk complete
+  uint64_t* hid_ready = a_full + 6;             // [2] hidden chunk written as the TMEM A operand
+  uint64_t* acc2_full = a_full + 8;             // M2 of the tile's last chunk complete
+  uint64_t* acc2_empty = a_full + 9;            // final epilogue has read acc2
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(a_full + 10);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) umma::tmem_alloc(tptr, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * TF_STAGES + 10; ++i) umma::mbar_init(bars + i, 1);
+  }
+  for (int i = tid; i < FF; i += TF_THREADS) sB1[i] = b1[i];
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tbase = *tptr;
+  const int nC = FF >> 7;                       // hidden chunks (even)
+  const long long n_tiles = (M + 127) >> 7;
+
+  if (warp == 9) {
+    // ---------------- TMA producer: stages in the order the MMA issuer consumes them ----------------
+    if (lane == 0) {
+      const uint32_t b0 = umma::smem_addr(tsm + TF_OFF_B);
+      uint32_t bi = 0;
+      auto push = [&](const uint8_t* src) {
+        const uint32_t st = bi % TF_STAGES;
+        if (bi >= TF_STAGES) umma::mbar_wait(b_empty + st, ((bi / TF_STAGES) - 1) & 1);
+        tg_mbar_expect_tx(b_full + st, 16384);
+        tg_bulk_g2s(b0 + st * 16384, src, 16384, b_full + st);
+        ++bi;
+      };
+      auto push_chunk = [&](const uint8_t* t0) {       // two 32 KB tiles [hi | lo]: lo halves first, then hi halves
+        push(t0 + 16384); push(t0 + 32768 + 16384); push(t0); push(t0 + 32768);
+      };
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        push_chunk(W1s);
+        for (int j = 0; j < nC; ++j) {
+          if (j + 1 < nC) push_chunk(W1s + (size_t)(j + 1) * 65536);      // W1 n-tile j + 1: K = 128 -> two tiles
+          push_chunk(W2s + (size_t)j * 65536);                            // W2 (one n-tile): k-blocks 2 j, 2 j + 1
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = umma::make_idesc_f16(128, 128);
+      const uint32_t a0 = umma::smem_addr(aBuf), b0 = umma::smem_addr(tsm + TF_OFF_B);
+      uint32_t bi = 0, g = 0, ti = 0;
+      // one 128-wide contraction from four weight stages (lo kb0, lo kb1, hi kb0, hi kb1); SS: A from shared memory,
+      // otherwise A = hidden chunk in tensor memory (hi words of k < 64 at +0, lo at +32, k >= 64 at +64 / +96)
+      auto contract = [&](bool ss, uint32_t aHi, uint32_t aLo, uint32_t d_main, uint32_t d_cross, bool first) {
+        bool acc_cross = !first, acc_main = !first || d_main == d_cross;
+        // one pass over a 64-wide k-block: 4 MMAs, A part (hi / lo) x the stage's B half
+        auto pass = [&](uint32_t bS, int kb, bool use_alo, uint32_t d, bool& accf) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int ks = kb * 4 + kk;                 // k16-step inside the 128-wide contraction
+            const uint64_t bd = umma::make_desc(bS + kk * 4096, 2048, 128);
+            if (ss) {
+              umma::mma_f16_ss(d, umma::make_desc((use_alo ? aLo : aHi) + ks * 4096, 2048, 128), bd, idesc, accf);
+            } else {
+              const uint32_t col = (ks < 4 ? 8u * ks : 64u + 8u * (ks - 4)) + (use_alo ? 32u : 0u);
+              umma::mma_f16_ts(d, aHi + col, bd, idesc, accf);
+            }
+            accf = true;
+          }
+        };
+        uint32_t stS[4];
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx) stS[sidx] = (bi + sidx) % TF_STAGES;
+        // lo stages: A_hi B_lo
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+          umma::mbar_wait(b_full + stS[sidx], ((bi + sidx) / TF_STAGES) & 1);
+          umma::fence_after_sync();
+          pass(b0 + stS[sidx] * 16384, sidx, false, d_cross, acc_cross);
+          umma::commit(b_empty + stS[sidx]);
+        }
+        // hi stages: A_lo B_hi over the whole contraction, then A_hi B_hi (every cross term before the large products)
+#pragma unroll
+        for (int sidx = 2; sidx < 4; ++sidx) {
+          umma::mbar_wait(b_full + stS[sidx], ((bi + sidx) / TF_STAGES) & 1);
+          umma::fence_after_sync();
+          pass(b0 + stS[sidx] * 16384, sidx & 1, true, d_cross, acc_cross);
+        }
+#pragma unroll
+        for (int sidx = 2; sidx < 4; ++sidx) {
+          pass(b0 + stS[sidx] * 16384, sidx & 1, false, d_main, acc_main);
+          umma::commit(b_empty + stS[sidx]);
+        }
+        bi += 4;
+      };
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t slot = ti & 1;
+        umma::mbar_wait(a_full + slot, (ti >> 1) & 1);
+        umma::fence_after_sync();
+        const uint32_t aHi = a0 + slot * TG_A_BYTES, aLo = aHi + 32768;
+        auto m1 = [&](uint32_t gg) {
+          const uint32_t set = tbase + (gg & 1) * 128;
+          contract(true, aHi, aLo, set, set, true);
+          umma::commit(acc1_full + (gg & 1));
+        };
+        m1(g);
+        for (int j = 0; j < nC; ++j, ++g) {
+          if (j + 1 < nC) m1(g + 1);
+          else umma::commit(a_empty + slot);            // every M1 of the tile issued: the x1 block is free once they complete
+          umma::mbar_wait(hid_ready + (g & 1), (g >> 1) & 1);
+          if (j == 0 && ti >= 1) umma::mbar_wait(acc2_empty, (ti - 1) & 1);
+          umma::fence_after_sync();
+          contract(false, tbase + (g & 1) * 128, 0, tbase + 256, tbase + 384, j == 0);
+        }
+        umma::commit(acc2_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- builders: x1 block of the tile -> fp16 hi/lo operand (slot = tile parity) ----------------
+    const int bw = warp - 4, r8 = lane & 7, cj = bw * 4 + (lane >> 3);        // k in [8 cj, 8 cj + 8)
+    uint32_t ti = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const long long m0 = tile * 128;
+      const uint32_t slot = ti & 1;
+      uint8_t* aHi = aBuf + slot * TG_A_BYTES;
+      uint8_t* aLo = aHi + 32768;
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const long long row = m0 + (hb * 8 + it) * 8 + r8;
+          const float* src = X + row * E + cj * 8;
+          if (row < M) {
+            v[2 * it] = *reinterpret_cast<const float4*>(src);
+            v[2 * it + 1] = *reinterpret_cast<const float4*>(src + 4);
+          } else {
+            v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (hb == 0 && ti >= 2) umma::mbar_wait(a_empty + slot, ((ti >> 1) - 1) & 1);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          uint4 h, l;
+          umma::split2_f16(v[2 * it].x, v[2 * it].y, h.x, l.x);
+          umma::split2_f16(v[2 * it].z, v[2 * it].w, h.y, l.y);
+          umma::split2_f16(v[2 * it + 1].x, v[2 * it + 1].y, h.z, l.z);
+          umma::split2_f16(v[2 * it + 1].z, v[2 * it + 1].w, h.w, l.w);
+          const uint32_t off = (uint32_t)cj * 2048u + (uint32_t)(hb * 8 + it) * 128u + (uint32_t)r8 * 16u;
+          *reinterpret_cast<uint4*>(aHi + off) = h;
+          *reinterpret_cast<uint4*>(aLo + off) = l;
+        }
+      }
+      umma::fence_async_smem();
+      tf_group_sync(1);
+      if (tid == 128) tg_mbar_arrive(a_full + slot);
+    }
+  } else {
+    // ---------------- epilogue warps: TMEM lane = row, warp = lane quadrant ----------------
+    float* stg = reinterpret_cast<float*>(tsm + TF_OFF_STG + warp * 4096);     // [32 rows][8 float4], float4 index ^ (row & 7)
+    const int er = lane >> 3, ec = lane & 7;
+    const uint32_t tl = tbase + ((uint32_t)(32 * warp) << 16);
+    float4 rr[8];                             // residual (x1) rows of the next 32-column chunk of the final epilogue
+    auto fetch_res = [&](long long tile, int c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long row = tile * 128 + 32 * warp + 4 * k + er;
+        rr[k] = (tile < n_tiles && row < M) ? *reinterpret_cast<const float4*>(X + (size_t)row * E + c * 32 + 4 * ec)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    uint32_t g = 0, ti = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const long long myrow = tile * 128 + 32 * warp + lane;
+      for (int j = 0; j < nC; ++j, ++g) {
+        // ---- E(j): accumulator row -> + b1, ReLU -> fp16 hi/lo A operand, in place ----
+        const uint32_t set = tl + (g & 1) * 128;
+        umma::mbar_wait(acc1_full + (g & 1), (g >> 1) & 1);
+        umma::fence_after_sync();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {                // hidden columns [64 hh, 64 hh + 64) of the chunk
+          uint32_t v[64];
+          umma::ld32_nw(set + 64 * hh, v);
+          umma::ld32_nw(set + 64 * hh + 32, v + 32);
+          umma::wait_ld();
+          uint32_t hw[32], lw[32];
+          const float* bp = sB1 + j * 128 + 64 * hh;
+          float* hp = hid_out && myrow < M ? hid_out + (size_t)myrow * FF + j * 128 + 64 * hh : nullptr;
+#pragma unroll
+          for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bp + 4 * c4);
+            float4 o;
+            o.x = fmaxf(umma::after_wait(v[4 * c4]) + bb.x, 0.f);
+            o.y = fmaxf(umma::after_wait(v[4 * c4 + 1]) + bb.y, 0.f);
+            o.z = fmaxf(umma::after_wait(v[4 * c4 + 2]) + bb.z, 0.f);
+            o.w = fmaxf(umma::after_wait(v[4 * c4 + 3]) + bb.w, 0.f);
+            if (hp) *reinterpret_cast<float4*>(hp + 4 * c4) = o;          // training keeps the hidden activations
+            umma::split2_f16(o.x, o.y, hw[2 * c4], lw[2 * c4]);
+            umma::split2_f16(o.z, o.w, hw[2 * c4 + 1], lw[2 * c4 + 1]);
+          }
+          umma::st16s<1>(set + 64 * hh, hw);
+          umma::st16s<1>(set + 64 * hh + 16, hw + 16);
+          umma::st16s<1>(set + 64 * hh + 32, lw);
+          umma::st16s<1>(set + 64 * hh + 48, lw + 16);
+        }
+        umma::wait_st();
+        umma::fence_before_sync();
+        tf_group_sync(2);
+        if (tid == 0) tg_mbar_arrive(hid_ready + (g & 1));
+        if (j == nC - 2) fetch_res(tile, 0);            // residual rows of the final epilogue's first chunk
+      }
+      // ---- F: out = acc2 + acc2 cross + b2 + x1 ----
+      umma::mbar_wait(acc2_full, ti & 1);
+      umma::fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const float4 bb = *reinterpret_cast<const float4*>(b2 + c * 32 + 4 * ec);
+        uint32_t v[32], v2[32];
+        umma::ld32_nw(tl + 256 + c * 32, v);
+        umma::ld32_nw(tl + 384 + c * 32, v2);
+        umma::wait_ld();
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 o;
+          o.x = umma::after_wait(v[4 * i4]) + umma::after_wait(v2[4 * i4]);
+          o.y = umma::after_wait(v[4 * i4 + 1]) + umma::after_wait(v2[4 * i4 + 1]);
+          o.z = umma::after_wait(v[4 * i4 + 2]) + umma::after_wait(v2[4 * i4 + 2]);
+          o.w = umma::after_wait(v[4 * i4 + 3]) + umma::after_wait(v2[4 * i4 + 3]);
+          *reinterpret_cast<float4*>(stg + lane * 32 + 4 * (i4 ^ (lane & 7))) = o;
+        }
+        if (c == 3) {                                   // acc2 is in registers / staging: the next tile's M2(0) may overwrite it
+          umma::fence_before_sync();
+          tf_group_sync(2);
+          if (tid == 0) tg_mbar_arrive(acc2_empty);
+        }
+        __syncwarp();
+        float4 o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = 4 * k + er;
+          o[k] = *reinterpret_cast<const float4*>(stg + r * 32 + 4 * (ec ^ (r & 7)));
+          o[k].x += bb.x + rr[k].x; o[k].y += bb.y + rr[k].y; o[k].z += bb.z + rr[k].z; o[k].w += bb.w + rr[k].w;
+        }
+        if (c < 3) fetch_res(tile, c + 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long row = tile * 128 + 32 * warp + 4 * k + er;
+          if (row < M) *reinterpret_cast<float4*>(out + (size_t)row * E + c * 32 + 4 * ec) = o[k];
+        }
+        __syncwarp();
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+static int tc_ffn(const float* x1, const float* derived, long long off_w1, long long off_w2, const float* b1, const float* b2,
+                  float* out, float* hid_out, long long rows, int ff, cudaStream_t st) {
+  ELG_REQUIRE(ff % 256 == 0 && ff <= TF_MAX_FF, ELG_EUNSUPPORTED, "tc_ffn: ff must be a multiple of 256, at most %d (got %d)", TF_MAX_FF, ff);
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    ELG_CUDA_OK(cudaFuncSetAttribute(tc_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));
+    int dev = 0;
+    ELG_CUDA_OK(cudaGetDevice(&dev));
+    ELG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr = true;
+  }
+  const long long tiles = (rows + 127) / 128;
+  tc_ffn_kernel<<<(unsigned)(tiles < sms ? tiles : sms), TF_THREADS, TF_SMEM, st>>>(
+      x1, reinterpret_cast<const uint8_t*>(derived + off_w1), b1, reinterpret_cast<const uint8_t*>(derived + off_w2), b2, out,
+      hid_out, rows, ff);
+  ELG_LAUNCH_OK();
+  return ELG_OK;
+}
+
 // ---- encoder self-attention: one CTA per (aug-instance, head) --------------------------------------
 // qkv rows are [q(128) | k(128) | v(128)]; scores q.k/4, softmax over keys, weighted values.
 constexpr int ATT_TK = 512;     // keys staged per tile (64 KB of K+V)
@@ -869,8 +1174,13 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
     ELG_TRY(tc_gemm<EPI_BIAS_RES>(att, derived, so + 3LL * E * E, tt, w + y.bo, x, rows, E, E, E, st));
     instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt, w + y.n1w, w + y.n1b, N1, x1);
     ELG_LAUNCH_OK();
-    ELG_TRY(tc_gemm<EPI_BIAS_RELU>(x1, derived, so + 4LL * E * E, hid, w + y.b1, nullptr, rows, d->ff, E, d->ff, st));
-    ELG_TRY(tc_gemm<EPI_BIAS_RES>(hid, derived, so + 4LL * E * E + (long long)d->ff * E, tt2, w + y.b2, x1, rows, E, d->ff, E, st));
+    if (d->ff % 256 == 0 && d->ff <= TF_MAX_FF) {      // fused feed-forward block: the hidden activations stay on chip
+      ELG_TRY(tc_ffn(x1, derived, so + 4LL * E * E, so + 4LL * E * E + (long long)d->ff * E, w + y.b1, w + y.b2, tt2,
+                     saved ? hid : nullptr, rows, d->ff, st));
+    } else {
+      ELG_TRY(tc_gemm<EPI_BIAS_RELU>(x1, derived, so + 4LL * E * E, hid, w + y.b1, nullptr, rows, d->ff, E, d->ff, st));
+      ELG_TRY(tc_gemm<EPI_BIAS_RES>(hid, derived, so + 4LL * E * E + (long long)d->ff * E, tt2, w + y.b2, x1, rows, E, d->ff, E, st));
+    }
     instance_norm_kernel<<<(unsigned)B, E, 0, st>>>(tt2, w + y.n2w, w + y.n2b, N1, xout);
     ELG_LAUNCH_OK();
   }
