@@ -687,8 +687,8 @@ static int tc_gemm(const float* A, const float* derived, long long split_off, fl
 // cross terms in their own accumulator.  TMEM: [0,128) [128,256) acc1 / hid sets, [256,384) acc2, [384,512) acc2 cross.
 // Weight stages are the 16 KB hi or lo halves of the pre-split 32 KB (n-tile, 64-wide k-block) tiles.
 // Warps 0-3 epilogue, 4-7 builders (x1 block of the next tile), 8 MMA issuer, 9 TMA producer; persistent over m-tiles.
-constexpr int TF_STAGES = 5, TF_THREADS = 320;
-constexpr int TF_OFF_B = 2 * TG_A_BYTES, TF_OFF_STG = TF_OFF_B + TF_STAGES * 16384, TF_OFF_B1 = TF_OFF_STG + 4 * 4096;
+constexpr int TF_STAGES = 9, TF_THREADS = 320;
+constexpr int TF_OFF_B = TG_A_BYTES, TF_OFF_STG = TF_OFF_B + TF_STAGES * 16384, TF_OFF_B1 = TF_OFF_STG + 4 * 4096;
 constexpr int TF_MAX_FF = 512;
 constexpr int TF_OFF_BAR = TF_OFF_B1 + TF_MAX_FF * 4, TF_SMEM = TF_OFF_BAR + 256;
 static_assert(TF_SMEM <= 232448, "tc_ffn_kernel shared memory");
@@ -798,8 +798,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_ffn_kernel(const float* __re
         bi += 4;
       };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t slot = ti & 1;
-        umma::mbar_wait(a_full + slot, (ti >> 1) & 1);
+        const uint32_t slot = 0;
+        umma::mbar_wait(a_full + slot, ti & 1);
         umma::fence_after_sync();
         const uint32_t aHi = a0 + slot * TG_A_BYTES, aLo = aHi + 32768;
         auto m1 = [&](uint32_t gg) {
@@ -809,8 +809,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_ffn_kernel(const float* __re
         };
         m1(g);
         for (int j = 0; j < nC; ++j, ++g) {
-          if (j + 1 < nC) m1(g + 1);
-          else umma::commit(a_empty + slot);            // every M1 of the tile issued: the x1 block is free once they complete
+          if (j + 1 < nC) {
+            m1(g + 1);
+            if (j + 2 == nC) umma::commit(a_empty + slot);      // every M1 of the tile issued: the x1 block is free once they complete
+          }
           umma::mbar_wait(hid_ready + (g & 1), (g >> 1) & 1);
           if (j == 0 && ti >= 1) umma::mbar_wait(acc2_empty, (ti - 1) & 1);
           umma::fence_after_sync();
@@ -825,7 +827,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_ffn_kernel(const float* __re
     uint32_t ti = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const long long m0 = tile * 128;
-      const uint32_t slot = ti & 1;
+      const uint32_t slot = 0;      // one x1 operand block: rewritten while the tile's last M2 contractions run
       uint8_t* aHi = aBuf + slot * TG_A_BYTES;
       uint8_t* aLo = aHi + 32768;
 #pragma unroll
@@ -842,7 +844,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_ffn_kernel(const float* __re
             v[2 * it] = v[2 * it + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (hb == 0 && ti >= 2) umma::mbar_wait(a_empty + slot, ((ti >> 1) - 1) & 1);
+        if (hb == 0 && ti >= 1) umma::mbar_wait(a_empty + slot, (ti - 1) & 1);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           uint4 h, l;
