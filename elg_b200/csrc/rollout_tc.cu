@@ -33,6 +33,7 @@
 //               [256,256+2*N1p) S / P buffers of the two groups, later the score accumulator
 //   during L (before the first Q K^T): [128,192) partial (sum, g) of the four sequence quarters, later [pem | z]
 //               [192,224) ol hi|lo   [224,256) head maxima + neighbour bits of the four quarters   [256,256+4*KT) local softmax weights hi|lo per head   [448,512) vps accumulators
+#include <cstdlib>
 #include "rollout_common.cuh"
 
 namespace elg {
@@ -1026,6 +1027,12 @@ int rollout_tc_tiles(const elg_model_desc* d, int B, int M, int N1, int* mt_out)
   const int cap = rollout_tc_max_rows(d, N1);
   if (cap == 0) return 0;
   int tiles = (M + cap - 1) / cap;
+  // Splitting the rows of an instance over several CTAs does not pay: a step of a 52-row tile takes 97 % of the time of a
+  // 100-row tile (latency-bound phases; tools/small_batch_timing.py: 64 aug-instances 5.30 ms as one tile, 5.15 ms as two).
+  if (const char* e = getenv("ELG_TC_TILES")) {        // diagnostic override (tools/small_batch_timing.py)
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8 && v * cap >= M) tiles = v;
+  }
   int mt = (((M + tiles - 1) / tiles) + 3) & ~3;
   if (mt > cap) { mt = cap; tiles = (M + mt - 1) / mt; }
   if (mt_out) *mt_out = mt;
