@@ -184,3 +184,29 @@ def test_model_without_local_policy_matches_oracle(kind):
     same = (a == b).all(dim=2)
     assert float(same.float().mean()) >= 0.97
     assert float(((reward.cpu() - ref_r).abs() / ref_r.abs())[same].max()) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["cvrp", "tsp"])
+def test_encoder_tables_do_not_depend_on_the_batch(kind):
+    """The persistent encoder kernels (tc_gemm_kernel, tc_ffn_kernel: one CTA per SM walking 128-row tiles through mbarrier
+    rings) give every instance the same tables whether it is encoded in a batch of 200 (20,200 rows = 158 tiles: several
+    tiles per CTA, a partial last tile, instances straddling tile boundaries) or in a batch of 3 (one CTA, partial tiles)."""
+    from elg_b200 import engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    handle = engine.ModelHandle(kind, mp, synthetic_state_dict(kind, seed=11, gain=2.0), DEV)
+    n = 200
+    if kind == "cvrp":
+        d = {k: v.to(DEV) for k, v in synthetic_cvrp_batch(n, 100, seed=7).items()}
+        xy, dem = engine.load_problems("cvrp", d["loc"], d["depot"], d["demand"], aug=1)
+    else:
+        xy, dem = engine.load_problems("tsp", synthetic_tsp_batch(n, 100, seed=7).to(DEV), aug=1)
+    big = engine.encode(handle, xy, dem)
+    torch.cuda.synchronize()
+    for lo in (0, 98, 197):
+        sl = slice(lo, lo + 3)
+        small = engine.encode(handle, xy[sl].contiguous(), None if dem is None else dem[sl].contiguous())
+        torch.cuda.synchronize()
+        for name in ("enc", "k", "v", "qtab", "eb") + (("qfirst",) if kind == "tsp" else ()):
+            a, b = getattr(big, name)[sl], getattr(small, name)
+            assert torch.equal(a, b), (name, lo, float((a - b).abs().max()))
