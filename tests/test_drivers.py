@@ -127,3 +127,26 @@ def test_test_py_loop_matches_oracle_costs(kind, capsys):
     avg = test([batch], model, env, 8)
     assert abs(float(avg) - float(ref_aug.mean())) < 1e-4 * float(ref_aug.mean())
     assert "Aug cost" in capsys.readouterr().out
+
+
+def test_lib_driver_gap_bins_and_records(tmp_path):
+    """Host helpers shared by the two library drivers (elg_b200/lib_driver.py): size bins as the reference prints them
+    (CVRP/test_vrplib.py:86-109: (0, 200], (200, 500], (500, ...)), record fields of the result file, JSON dump."""
+    import json
+    from elg_b200 import lib_driver as drv
+    res = []
+    for name, scale, opt, cost in (("a", 100, 100.0, 105.0), ("b", 200, 50.0, 51.0), ("c", 201, 10.0, 11.0), ("d", 900, 1000.0, 1100.0)):
+        rec = {"run_idx": 0}
+        drv.fill_record(rec, cost, scale, opt)
+        assert rec["best_cost"] == cost and rec["scale"] == scale and abs(rec["gap"] - (cost - opt) / opt) < 1e-12
+        res.append({"instance": name, "optimal": opt, "record": [rec]})
+    drv.fill_record(None, 1.0, 1, 1.0)                       # the reference passes result_dict=None in ad-hoc calls
+    bins = drv.gap_bins(res, [("<200", 0, 200), ("200-500", 200, 500), ("500-1000", 500, 10 ** 9)])
+    assert abs(bins["<200"] - 100 * (0.05 + 0.02) / 2) < 1e-9          # scale 200 belongs to the first bin
+    assert abs(bins["200-500"] - 10.0) < 1e-9 and abs(bins["500-1000"] - 10.0) < 1e-9
+    assert abs(bins["total"] - 100 * (0.05 + 0.02 + 0.1 + 0.1) / 4) < 1e-9
+    assert "200-500" not in drv.gap_bins(res[:2], [("<200", 0, 200), ("200-500", 200, 500)])    # empty bins are not reported
+    drv.dump_results(res, str(tmp_path / "out"), "x.json")
+    assert json.load(open(tmp_path / "out" / "x.json"))[3]["record"][0]["scale"] == 900
+    with pytest.raises(RuntimeError):
+        drv.require_cuda({"use_cuda": False, "cuda_device_num": 0})
