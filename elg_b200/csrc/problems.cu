@@ -62,14 +62,14 @@ __global__ void pairwise_dist_kernel(const float* __restrict__ xy, int B, int N1
 // for tsp) ordered by (distance from i, index).  The decode step takes the first k *valid* entries,
 // which is what torch.topk(k, largest=False) over the masked distance row yields in the reference
 // (CVRP/models.py:74,375; TSP/models.py:62,286) -- computed once instead of twice per step.
-__global__ void neighbour_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand, int N1,
-                                 uint8_t* __restrict__ nbr) {
-  __shared__ float sd[128];
+__global__ void __launch_bounds__(128) neighbour_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand, int N1,
+                                                        uint8_t* __restrict__ nbr) {
+  __shared__ __align__(16) uint32_t skey[128];      // rank keys: distance bits (non-negative floats order like integers), +inf for non-candidates
+  __shared__ int scnt[128];                         // candidates per "strictly smaller" count: > 1 marks a group of equal distances
   const int i = blockIdx.x % N1, b = blockIdx.x / N1;
   const float* p = xy + (size_t)b * N1 * 2;
   const int j0 = problem == ELG_CVRP ? 1 : 0;
   const float xi = p[2 * i], yi = p[2 * i + 1];
-  for (int j = threadIdx.x; j < N1; j += blockDim.x) sd[j] = dist2(xi - p[2 * j], yi - p[2 * j + 1]);
   uint8_t* row = nbr + ((size_t)b * N1 + i) * ELG_NBR_NODE_BYTES(N1);
   for (int e = threadIdx.x; e < ELG_NBR_STRIDE; e += blockDim.x) row[e] = 0;
   // pair features of get_cur_feature (CVRP/CVRPEnv.py:291-318, TSP/TSPEnv.py:135-156) for cur = i: distance and
@@ -80,21 +80,38 @@ __global__ void neighbour_kernel(int problem, const float* __restrict__ xy, cons
   float4* rec = reinterpret_cast<float4*>(row + ELG_NBR_STRIDE + ELG_NBR_PAIR_BYTES(N1));
   // resident instances have N1 <= 112 <= blockDim.x: thread j owns node j (distance, angle computed once, used twice)
   const int j = threadIdx.x;
-  float thj = 0.f;
+  const bool cand = j >= j0 && j < N1;
+  float dj = 0.f, thj = 0.f;
   if (j < N1) {
+    dj = dist2(xi - p[2 * j], yi - p[2 * j + 1]);
     thj = atan2f(p[2 * j + 1] - yi, p[2 * j] - xi);
-    feat[j] = make_float2(sd[j], thj);
+    feat[j] = make_float2(dj, thj);
+  }
+  const uint32_t bj = __float_as_uint(dj);
+  skey[j] = cand ? bj : 0x7f800000u;
+  scnt[j] = 0;
+  __syncthreads();
+  // rank = candidates ordered by (distance, index) before me.  The strictly smaller ones are counted on the bit patterns,
+  // four keys per shared-memory load; equal distances (rare for random instances, common on integer library coordinates)
+  // show up as a "strictly smaller" count shared by several candidates and are resolved by index.
+  int lt = 0;
+  if (cand) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(skey);
+    const int n4 = (N1 + 3) >> 2;
+#pragma unroll 4
+    for (int c = 0; c < n4; ++c) {
+      const uint4 kk = k4[c];
+      lt += (kk.x < bj ? 1 : 0) + (kk.y < bj ? 1 : 0) + (kk.z < bj ? 1 : 0) + (kk.w < bj ? 1 : 0);
+    }
+    atomicAdd(&scnt[lt], 1);
   }
   __syncthreads();
-  if (j >= j0 && j < N1) {
-    const float dj = sd[j];
-    int rank = 0;
-    for (int k = j0; k < N1; ++k) {
-      const float dk = sd[k];
-      rank += (dk < dj) || (dk == dj && k < j);
-    }
-    row[nbr_pos(rank)] = (uint8_t)j;
-    rec[rank] = make_float4(dj, thj, demand ? demand[(size_t)b * N1 + j] : 0.f, __int_as_float(j));
+  if (cand) {
+    int r = lt;
+    if (scnt[lt] > 1)
+      for (int k = j0; k < j; ++k) r += skey[k] == bj ? 1 : 0;
+    row[nbr_pos(r)] = (uint8_t)j;
+    rec[r] = make_float4(dj, thj, demand ? demand[(size_t)b * N1 + j] : 0.f, __int_as_float(j));
   }
   for (int e = N1 - j0 + threadIdx.x; e < N1; e += blockDim.x) rec[e] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
