@@ -210,3 +210,40 @@ def test_encoder_tables_do_not_depend_on_the_batch(kind):
         for name in ("enc", "k", "v", "qtab", "eb") + (("qfirst",) if kind == "tsp" else ()):
             a, b = getattr(big, name)[sl], getattr(small, name)
             assert torch.equal(a, b), (name, lo, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("kind", ["cvrp", "tsp"])
+def test_decoder_tables_with_separately_allocated_buffers(kind):
+    """elg_encode writes K', V, qtab (qfirst) in ONE GEMM launch when the caller's buffers are equally spaced planes (the
+    Python engine's are) and in one launch per table otherwise (any C-ABI caller with its own allocations): same bits."""
+    import ctypes as C
+    from elg_b200 import _lib, engine
+    from elg_b200.synth import DEFAULT_MODEL_PARAMS, synthetic_cvrp_batch, synthetic_state_dict, synthetic_tsp_batch
+    mp = dict(DEFAULT_MODEL_PARAMS[kind])
+    handle = engine.ModelHandle(kind, mp, synthetic_state_dict(kind, seed=12, gain=2.0), DEV)
+    if kind == "cvrp":
+        d = {k: v.to(DEV) for k, v in synthetic_cvrp_batch(5, 60, seed=8).items()}
+        xy, dem = engine.load_problems("cvrp", d["loc"], d["depot"], d["demand"], aug=8)
+    else:
+        xy, dem = engine.load_problems("tsp", synthetic_tsp_batch(5, 60, seed=8).to(DEV), aug=8)
+    ref = engine.encode(handle, xy, dem)
+    torch.cuda.synchronize()
+    other = engine.EncodedBatch(handle, xy, dem)
+    n = ref.k.numel()
+    buf = torch.empty(4 * n + 4096, device=DEV)               # tables carved out at irregular (16-byte aligned) offsets
+    other.k = buf[0:n].view_as(ref.k)
+    other.v = buf[n + 256:2 * n + 256].view_as(ref.k)
+    other.qtab = buf[2 * n + 1024:3 * n + 1024].view_as(ref.k)
+    if kind == "tsp":
+        other.qfirst = buf[3 * n + 2048:4 * n + 2048].view_as(ref.k)
+    assert other.v.data_ptr() - other.k.data_ptr() != other.qtab.data_ptr() - other.v.data_ptr()
+    other.tables = _lib.Tables(*[engine._ptr(x).value for x in (other.xy, other.demand, other.unscaled, other.enc, other.k, other.v,
+                                                                 other.e, other.eb, other.qtab, other.qfirst, other.nbr, other.et, None)])
+    nbytes = int(_lib.lib.elg_encode_workspace_bytes(handle.desc, other.B, other.N1))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    with torch.cuda.device(DEV):
+        _lib.check(_lib.lib.elg_encode(handle.desc, engine._ptr(handle.weights), engine._ptr(handle.derived), other.tables, other.B,
+                                       other.N1, engine._ptr(ws), nbytes, engine._stream(torch.device(DEV))))
+    torch.cuda.synchronize()
+    for name in ("enc", "k", "v", "qtab", "eb", "e") + (("qfirst",) if kind == "tsp" else ()):
+        assert torch.equal(getattr(ref, name), getattr(other, name)), name
