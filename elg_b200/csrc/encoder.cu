@@ -313,30 +313,42 @@ __global__ void __launch_bounds__(128, 3) enc_attention_tc_kernel(const float* _
 // ---- decoder keys / values as fp16 hi/lo tcgen05 B operands (rollout_tc.cu), segments 1 and 2 of elg_tables.e ----
 //   K'  [N1p keys x 128 k]  element (j, c) at (c/8)*N1p*16 + (j/8)*128 + (j%8)*16 + (c%8)*2        (like E')
 //   V^T per head h: [16 d x N1p keys]  element (d, j) at h*N1p*32 + (j/8)*256 + (d/8)*128 + (d%8)*16 + (j%8)*2
-// each as [hi | lo] halves of N1p*256 bytes.  One CTA per aug-instance; padded keys stay zero (memset by the caller).
+// each as [hi | lo] halves of N1p*256 bytes.  One CTA per aug-instance; padded key slots are written as zeros.
 __global__ void __launch_bounds__(256) split_kv_kernel(const float* __restrict__ K, const float* __restrict__ V,
                                                        uint8_t* __restrict__ ops, int N1) {
   const int N1p = (N1 + 15) & ~15;
   const size_t b = blockIdx.x;
   const float* kp = K + b * N1 * E;
   const float* vp = V + b * N1 * E;
-  uint8_t* ko = ops + b * 3 * ((size_t)N1p * 512) + (size_t)N1p * 512;
+  uint8_t* eo = ops + b * 3 * ((size_t)N1p * 512);
+  uint8_t* ko = eo + (size_t)N1p * 512;
   uint8_t* vo = ko + (size_t)N1p * 512;
   const uint32_t half = (uint32_t)N1p * 256u;
-  for (int i = threadIdx.x; i < N1 * (E / 2); i += 256) {        // K': column pairs of one key -> one 32-bit word
-    const int j = i / (E / 2), c = (i % (E / 2)) * 2;
-    const float2 v = *reinterpret_cast<const float2*>(kp + (size_t)j * E + c);
-    __half h0, l0, h1, l1;
-    umma::split_f16(v.x, h0, l0);
-    umma::split_f16(v.y, h1, l1);
-    const uint32_t off = umma::elem_off(j, c, (uint32_t)N1p * 16u);
-    *reinterpret_cast<uint32_t*>(ko + off) = umma::pack_h2(h0, h1);
-    *reinterpret_cast<uint32_t*>(ko + half + off) = umma::pack_h2(l0, l1);
+  // K': unit = (key j, 8-column chunk): 32 bytes in, one 16-byte core-matrix row of hi and of lo out; j % 8 fastest, so eight
+  // lanes fill 128 contiguous bytes.  Key slots N1 .. N1p-1 are written as zeros here -- for K' and for E' (whose live rows
+  // come from the GEMM epilogue) -- so the caller needs no memset of the operand buffer.
+  for (int i = threadIdx.x; i < N1p * (E / 8); i += 256) {
+    const int j = (i & 7) + ((i >> 3) / (E / 8)) * 8, c8 = (i >> 3) % (E / 8);
+    const uint32_t off = (uint32_t)c8 * (uint32_t)N1p * 16u + (uint32_t)(j >> 3) * 128u + (uint32_t)(j & 7) * 16u;
+    uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+    if (j < N1) {
+      const float4 a = *reinterpret_cast<const float4*>(kp + (size_t)j * E + c8 * 8);
+      const float4 c = *reinterpret_cast<const float4*>(kp + (size_t)j * E + c8 * 8 + 4);
+      umma::split2_f16(a.x, a.y, h.x, l.x);
+      umma::split2_f16(a.z, a.w, h.y, l.y);
+      umma::split2_f16(c.x, c.y, h.z, l.z);
+      umma::split2_f16(c.z, c.w, h.w, l.w);
+    } else {
+      *reinterpret_cast<uint4*>(eo + off) = h;
+      *reinterpret_cast<uint4*>(eo + half + off) = h;
+    }
+    *reinterpret_cast<uint4*>(ko + off) = h;
+    *reinterpret_cast<uint4*>(ko + half + off) = l;
   }
-  const int jp = (N1 + 1) >> 1;
+  const int jp = N1p >> 1;
   for (int i = threadIdx.x; i < jp * E; i += 256) {               // V^T: key pairs of one (head, d) -> one 32-bit word
     const int c = i % E, j = (i / E) * 2;
-    const float a = vp[(size_t)j * E + c];
+    const float a = j < N1 ? vp[(size_t)j * E + c] : 0.f;
     const float bq = j + 1 < N1 ? vp[(size_t)(j + 1) * E + c] : 0.f;
     __half h0, l0, h1, l1;
     umma::split_f16(a, h0, l0);
@@ -1239,7 +1251,6 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
     ELG_TRY(tc_gemm<EPI_NONE>(enc, derived, sd + 1LL * E * E, t->v, nullptr, nullptr, rows, E, E, E, st));
   }
   if (rollout_is_resident(d, N1)) {
-    ELG_CUDA_OK(cudaMemsetAsync(t->e, 0, elg_e_bytes(d, B, N1), st));      // padded rows of the MMA operand must be zero
     ELG_TRY(gemm<EPI_UMMA_SPLIT>(enc, derived + DER_WET, reinterpret_cast<float*>(t->e), nullptr, nullptr, rows, E, E, E, N1, st));
     split_kv_kernel<<<(unsigned)B, 256, 0, st>>>(t->k, t->v, reinterpret_cast<uint8_t*>(t->e), N1);
     ELG_LAUNCH_OK();
