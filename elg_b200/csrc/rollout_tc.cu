@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_tc_kernel(const RolloutArgs A) 
         }
         PHASE_MARK(9);
       }
-      __syncthreads();
+      quad_sync(11 + q);       // the four candidates of a row come from the four warps of its lane quadrant: no CTA-wide wait
 
       // ---- selection: first-max over the 4 column quarters (ties -> lowest index, as torch.argmax) ----------------
       int sl;
