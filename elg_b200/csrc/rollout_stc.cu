@@ -744,7 +744,9 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
             }
           }
           umma::fence_before_sync();
-          __syncthreads();
+          quad_sync_s(11 + q);      // the scratch row is written and read by the four threads of the row (one lane quadrant);
+                                    // the CTA barrier at the end of the iteration still orders the accumulator reads of all
+                                    // warps before the MMAs of the tile after next
           // the neighbours of this tile (and the depot) with their own penalty + local score; only the depot can be masked
           if (act) {
 #pragma unroll
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(RT, 1) rollout_stc_kernel(const RolloutArgs A)
         }
         PHASE_MARK(8);
         sX2[wsub * 128 + row] = make_float2(vbest, __int_as_float(ibest));
-        __syncthreads();
+        quad_sync_s(11 + q);        // candidates of a row: its lane quadrant only
         {
           float bv = -INFINITY;
           int bi = 0x7fffffff;
