@@ -27,26 +27,41 @@ int launch_neighbours(const elg_model_desc* d, const float* xy, const float* dem
 __global__ void embed_kernel(int problem, const float* __restrict__ xy, const float* __restrict__ demand,
                              const float* __restrict__ w, elg_weight_layout_t L, long long rows, int N1,
                              float* __restrict__ x) {
-  const long long total = rows * E;
+  // thread = (node row, 4 channels): one 16-byte store; the row -> node index modulo is paid once per four outputs
+  const long long total = rows * (E / 4);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(idx % E);
-    long long r = idx / E;
-    int j = (int)(r % N1);
-    float px = xy[2 * r], py = xy[2 * r + 1];
-    float v;
+    const int c0 = (int)(idx & (E / 4 - 1)) * 4;
+    const long long r = idx / (E / 4);
+    const int j = (int)(r % N1);
+    const float2 p = *reinterpret_cast<const float2*>(xy + 2 * r);
+    const float px = p.x, py = p.y;
+    float v[4];
     if (problem == ELG_CVRP) {
       if (j == 0) {
         // F.linear: x0*w0 + x1*w1 then + bias
-        v = fmaf(py, w[L.emb_depot_w + c * 2 + 1], px * w[L.emb_depot_w + c * 2]) + w[L.emb_depot_b + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + i;
+          v[i] = fmaf(py, w[L.emb_depot_w + c * 2 + 1], px * w[L.emb_depot_w + c * 2]) + w[L.emb_depot_b + c];
+        }
       } else {
-        v = fmaf(demand[r], w[L.emb_node_w + c * 3 + 2],
-                 fmaf(py, w[L.emb_node_w + c * 3 + 1], px * w[L.emb_node_w + c * 3])) + w[L.emb_node_b + c];
+        const float dm = demand[r];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + i;
+          v[i] = fmaf(dm, w[L.emb_node_w + c * 3 + 2], fmaf(py, w[L.emb_node_w + c * 3 + 1], px * w[L.emb_node_w + c * 3])) +
+                 w[L.emb_node_b + c];
+        }
       }
     } else {
-      v = fmaf(py, w[L.emb_node_w + c * 2 + 1], px * w[L.emb_node_w + c * 2]) + w[L.emb_node_b + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + i;
+        v[i] = fmaf(py, w[L.emb_node_w + c * 2 + 1], px * w[L.emb_node_w + c * 2]) + w[L.emb_node_b + c];
+      }
     }
-    x[idx] = v;
+    *reinterpret_cast<float4*>(x + r * E + c0) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -1194,7 +1209,7 @@ static int encode_impl(const elg_model_desc* d, const float* weights, const floa
   const float* w = weights;
 
   {
-    long long total = rows * E;
+    long long total = rows * (E / 4);
     int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     embed_kernel<<<grid, 256, 0, st>>>(d->problem, t->xy, t->demand, w, L, rows, N1, x);
     ELG_LAUNCH_OK();
